@@ -1,0 +1,200 @@
+// GroupNorm (+SiLU) and LayerNorm over channels-last bf16 activations; fp32 statistics.
+// HBM-bound streaming kernels: 16-byte vector accesses, fully coalesced rows.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <string>
+
+#include "common.cuh"
+#include "internal.h"
+#include "../../include/gligen_b200.h"
+
+namespace glg {
+
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  float2 f;
+  f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+  f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+  f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+  f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// ---- GroupNorm pass 1: per-(batch, group) sum and sum of squares -------------------------------
+// grid (chunks, B); blockDim = (C/8) * rpi, thread -> (fixed channel vector cv, row lane rl).
+__global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ stats,
+                                int HW, int C, int groups, int rows_per_chunk) {
+  extern __shared__ float gn_sm[];          // [2][C]
+  float* s_sum = gn_sm;
+  float* s_sq = gn_sm + C;
+  const int vec = C >> 3;
+  const int rpi = blockDim.x / vec;
+  const int cv = threadIdx.x % vec, rl = threadIdx.x / vec;
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) gn_sm[i] = 0.f;
+  __syncthreads();
+  const int r0 = blockIdx.x * rows_per_chunk;
+  const int r1 = min(HW, r0 + rows_per_chunk);
+  float a[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a[j] = 0.f; q[j] = 0.f; }
+  const bf16* xb = x + (long long)b * HW * ldx + cv * 8;
+  for (int r = r0 + rl; r < r1; r += rpi) {
+    float v[8];
+    load8(xb + (long long)r * ldx, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { atomicAdd(&s_sum[cv * 8 + j], a[j]); atomicAdd(&s_sq[cv * 8 + j], q[j]); }
+  __syncthreads();
+  const int cpg = C / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float s = 0.f, ss = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { s += s_sum[c]; ss += s_sq[c]; }
+    atomicAdd(&stats[((long long)b * groups + g) * 2 + 0], s);
+    atomicAdd(&stats[((long long)b * groups + g) * 2 + 1], ss);
+  }
+}
+
+// ---- GroupNorm pass 2: normalise + affine (+SiLU) -----------------------------------------------
+__global__ void gn_apply_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ stats, int HW, int C, int groups, float eps, int silu,
+                                int rows_per_chunk) {
+  extern __shared__ float gn_sm[];          // scale[C], shift[C]
+  float* s_a = gn_sm;
+  float* s_b = gn_sm + C;
+  const int b = blockIdx.y;
+  const int cpg = C / groups;
+  const float inv_n = 1.f / ((float)HW * (float)cpg);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float mean = stats[((long long)b * groups + g) * 2] * inv_n;
+    const float var = fmaxf(stats[((long long)b * groups + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float ga = gamma[c] * rstd;
+    s_a[c] = ga;
+    s_b[c] = beta[c] - mean * ga;
+  }
+  __syncthreads();
+  const int vec = C >> 3;
+  const int r0 = blockIdx.x * rows_per_chunk;
+  const int r1 = min(HW, r0 + rows_per_chunk);
+  const long long total = (long long)(r1 - r0) * vec;
+  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+    const int r = r0 + (int)(i / vec), cv = (int)(i % vec);
+    float v[8];
+    load8(x + ((long long)b * HW + r) * ldx + cv * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = fmaf(v[j], s_a[cv * 8 + j], s_b[cv * 8 + j]);
+      v[j] = silu ? silu_f(t) : t;
+    }
+    store8(y + ((long long)b * HW + r) * ldy + cv * 8, v);
+  }
+}
+
+// ---- LayerNorm: one warp per row, two-pass in registers ----------------------------------------
+template <int MAXV>
+__global__ void ln_kernel(const bf16* __restrict__ x, long long x_batch, bf16* __restrict__ y, long long y_batch,
+                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                          int rows, int C, float eps, long long total_rows) {
+  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= total_rows) return;
+  const int lane = threadIdx.x & 31;
+  const int b = (int)(gw / rows), r = (int)(gw % rows);
+  const bf16* xr = x + (long long)b * x_batch + (long long)r * C;
+  bf16* yr = y + (long long)b * y_batch + (long long)r * C;
+  const int vec = C >> 3;
+  float v[MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int cv = lane + i * 32;
+    if (cv < vec) {
+      load8(xr + cv * 8, v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int cv = lane + i * 32;
+    if (cv < vec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float dlt = v[i][j] - mean; ss = fmaf(dlt, dlt, ss); }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int cv = lane + i * 32;
+    if (cv < vec) {
+      float o[8];
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + cv * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + cv * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + cv * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + cv * 8 + 4));
+      o[0] = (v[i][0] - mean) * rstd * g0.x + b0.x; o[1] = (v[i][1] - mean) * rstd * g0.y + b0.y;
+      o[2] = (v[i][2] - mean) * rstd * g0.z + b0.z; o[3] = (v[i][3] - mean) * rstd * g0.w + b0.w;
+      o[4] = (v[i][4] - mean) * rstd * g1.x + b1.x; o[5] = (v[i][5] - mean) * rstd * g1.y + b1.y;
+      o[6] = (v[i][6] - mean) * rstd * g1.z + b1.z; o[7] = (v[i][7] - mean) * rstd * g1.w + b1.w;
+      store8(yr + cv * 8, o);
+    }
+  }
+}
+
+}  // namespace glg
+
+using namespace glg;
+
+extern "C" int glg_groupnorm(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma, const float* beta,
+                             float* stats, int32_t B, int32_t HW, int32_t C, int32_t groups, float eps, int32_t silu,
+                             void* stream) {
+  if (C % 8 || C % groups || (ldx % 8) || (ldy % 8)) return set_error("glg_groupnorm: C and leading dims must be multiples of 8, C % groups == 0");
+  if (C > 4096) return set_error("glg_groupnorm: C too large");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(float) * 2 * B * groups, st);
+  if (e != cudaSuccess) return set_error(std::string("glg_groupnorm memset: ") + cudaGetErrorString(e));
+  const int vec = C / 8;
+  int rpi = 256 / vec; if (rpi < 1) rpi = 1;
+  const int threads = vec * rpi;          // <= 512 for C <= 4096
+  if (threads > 1024) return set_error("glg_groupnorm: C too large for one block");
+  int chunks = (4 * 148 + B - 1) / B;
+  int max_chunks = (HW + rpi * 4 - 1) / (rpi * 4);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  const int rows_per_chunk = (HW + chunks - 1) / chunks;
+  chunks = (HW + rows_per_chunk - 1) / rows_per_chunk;
+  dim3 grid(chunks, B);
+  gn_stats_kernel<<<grid, threads, 2 * C * sizeof(float), st>>>((const bf16*)x, ldx, stats, HW, C, groups, rows_per_chunk);
+  count_launch();
+  if (check_launch("gn_stats launch")) return -1;
+  gn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), st>>>((const bf16*)x, ldx, (bf16*)y, ldy, gamma, beta, stats, HW, C, groups, eps, silu, rows_per_chunk);
+  count_launch();
+  return check_launch("gn_apply launch");
+}
+
+extern "C" int glg_layernorm(const void* x, int64_t x_batch, void* y, int64_t y_batch, const float* gamma, const float* beta,
+                             int32_t B, int32_t rows, int32_t C, float eps, void* stream) {
+  if (C % 8 || C > 2048) return set_error("glg_layernorm: C must be a multiple of 8 and <= 2048");
+  if ((x_batch % 8) || (y_batch % 8)) return set_error("glg_layernorm: batch strides must be multiples of 8");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = (long long)B * rows;
+  const int wpb = 8;
+  const unsigned grid = (unsigned)((total + wpb - 1) / wpb);
+  const int vec = C / 8;
+  if (vec <= 64) ln_kernel<2><<<grid, wpb * 32, 0, st>>>((const bf16*)x, x_batch, (bf16*)y, y_batch, gamma, beta, rows, C, eps, total);
+  else if (vec <= 160) ln_kernel<5><<<grid, wpb * 32, 0, st>>>((const bf16*)x, x_batch, (bf16*)y, y_batch, gamma, beta, rows, C, eps, total);
+  else ln_kernel<8><<<grid, wpb * 32, 0, st>>>((const bf16*)x, x_batch, (bf16*)y, y_batch, gamma, beta, rows, C, eps, total);
+  count_launch();
+  return check_launch("layernorm launch");
+}

@@ -1,0 +1,344 @@
+"""UNet configuration, block schedule and parameter inventory for the GLIGEN denoiser.
+
+This module is pure host-side bookkeeping (no torch ops on the hot path).  It restates
+*structure* only: which blocks exist, their channel counts, and the state-dict key of every
+parameter, so that a reference checkpoint loads verbatim.
+
+Reference: ldm/modules/diffusionmodules/openaimodel.py:238-397 (UNetModel.__init__),
+ldm/modules/attention.py:303-376, ldm/modules/diffusionmodules/{text,text_image,keypoint}_grounding_net.py.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from dataclasses import dataclass, field, replace
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+
+@dataclass(frozen=True)
+class UNetConfig:
+    image_size: int = 64
+    in_channels: int = 4
+    out_channels: int = 4
+    model_channels: int = 320
+    num_res_blocks: int = 2
+    attention_resolutions: Tuple[int, ...] = (4, 2, 1)
+    channel_mult: Tuple[int, ...] = (1, 2, 4, 4)
+    num_heads: int = 8
+    transformer_depth: int = 1
+    context_dim: int = 768
+    fuser_type: str = "gatedSA"
+    inpaint_mode: bool = False
+    # grounding tokenizer: "text" | "text_image" | "keypoint"
+    tokenizer: str = "text"
+    tok_in_dim: int = 768          # text / text_image: CLIP feature dim
+    tok_out_dim: int = 768
+    tok_hidden: int = 512          # hard-coded 512 in the reference PositionNets
+    fourier_freqs: int = 8
+    max_persons: int = 8           # keypoint only
+
+    @property
+    def time_embed_dim(self) -> int:
+        return self.model_channels * 4
+
+    @property
+    def first_conv_in(self) -> int:
+        # openaimodel.py:299-304
+        return self.in_channels * 2 + 1 if self.inpaint_mode else self.in_channels
+
+    @property
+    def position_dim(self) -> int:
+        ncoord = 2 if self.tokenizer == "keypoint" else 4
+        return self.fourier_freqs * 2 * ncoord
+
+    @property
+    def tok_feat_dim(self) -> int:
+        """Width of the non-positional part fed to the PositionNet MLP."""
+        return self.tok_out_dim if self.tokenizer == "keypoint" else self.tok_in_dim
+
+    def tokens_per_sample(self, max_objs: int) -> int:
+        return 2 * max_objs if self.tokenizer == "text_image" else max_objs
+
+
+SD14_BOX_TEXT = UNetConfig()
+SD14_BOX_TEXT_IMAGE = replace(SD14_BOX_TEXT, tokenizer="text_image")
+SD14_KEYPOINT = replace(SD14_BOX_TEXT, tokenizer="keypoint")
+SD14_INPAINT_BOX_TEXT = replace(SD14_BOX_TEXT, inpaint_mode=True)
+# Small structurally-identical model used by fast parity tests (every width still a multiple of 64
+# so that the tensor-core tiles apply; latent 16x16 -> levels 16/8/4/2).
+TINY = UNetConfig(image_size=16, model_channels=64, context_dim=128, tok_in_dim=128, tok_out_dim=128)
+TINY_TEXT_IMAGE = replace(TINY, tokenizer="text_image")
+TINY_KEYPOINT = replace(TINY, tokenizer="keypoint", max_persons=2)
+TINY_INPAINT = replace(TINY, inpaint_mode=True)
+
+NAMED_CONFIGS = {
+    "sd14_box_text": SD14_BOX_TEXT,
+    "sd14_box_text_image": SD14_BOX_TEXT_IMAGE,
+    "sd14_keypoint": SD14_KEYPOINT,
+    "sd14_inpaint_box_text": SD14_INPAINT_BOX_TEXT,
+    "tiny": TINY,
+    "tiny_text_image": TINY_TEXT_IMAGE,
+    "tiny_keypoint": TINY_KEYPOINT,
+    "tiny_inpaint": TINY_INPAINT,
+}
+
+
+# ----------------------------------------------------------------------------------------------
+# Block schedule
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class Layer:
+    kind: str                 # "conv_in" | "res" | "st" | "down" | "up"
+    prefix: str               # state-dict prefix, e.g. "input_blocks.1.0"
+    cin: int = 0
+    cout: int = 0
+    heads: int = 0
+    d_head: int = 0
+
+
+@dataclass
+class Block:
+    where: str                # "in" | "mid" | "out"
+    index: int
+    layers: List[Layer] = field(default_factory=list)
+    ds: int = 1               # downsample factor of the block's *input* resolution
+    skip_ch: int = 0          # (output blocks) channels popped from the skip stack
+    out_ch: int = 0
+    out_ds: int = 1
+
+
+def block_schedule(cfg: UNetConfig) -> List[Block]:
+    """Enumerate input/middle/output blocks exactly as openaimodel.py:305-388 builds them."""
+    mc = cfg.model_channels
+    blocks: List[Block] = []
+    b0 = Block("in", 0, [Layer("conv_in", "input_blocks.0.0", cfg.first_conv_in, mc)], ds=1, out_ch=mc, out_ds=1)
+    blocks.append(b0)
+    chans = [mc]
+    ch, ds = mc, 1
+    idx = 1
+    for level, mult in enumerate(cfg.channel_mult):
+        for _ in range(cfg.num_res_blocks):
+            blk = Block("in", idx, ds=ds)
+            blk.layers.append(Layer("res", f"input_blocks.{idx}.0", ch, mult * mc))
+            ch = mult * mc
+            if ds in cfg.attention_resolutions:
+                blk.layers.append(Layer("st", f"input_blocks.{idx}.1", ch, ch, cfg.num_heads, ch // cfg.num_heads))
+            blk.out_ch, blk.out_ds = ch, ds
+            blocks.append(blk)
+            chans.append(ch)
+            idx += 1
+        if level != len(cfg.channel_mult) - 1:
+            blk = Block("in", idx, [Layer("down", f"input_blocks.{idx}.0", ch, ch)], ds=ds, out_ch=ch, out_ds=ds * 2)
+            blocks.append(blk)
+            chans.append(ch)
+            ds *= 2
+            idx += 1
+    mid = Block("mid", 0, ds=ds, out_ch=ch, out_ds=ds)
+    mid.layers = [
+        Layer("res", "middle_block.0", ch, ch),
+        Layer("st", "middle_block.1", ch, ch, cfg.num_heads, ch // cfg.num_heads),
+        Layer("res", "middle_block.2", ch, ch),
+    ]
+    blocks.append(mid)
+    oidx = 0
+    for level, mult in list(enumerate(cfg.channel_mult))[::-1]:
+        for i in range(cfg.num_res_blocks + 1):
+            ich = chans.pop()
+            blk = Block("out", oidx, ds=ds, skip_ch=ich)
+            blk.layers.append(Layer("res", f"output_blocks.{oidx}.0", ch + ich, mc * mult))
+            ch = mc * mult
+            j = 1
+            if ds in cfg.attention_resolutions:
+                blk.layers.append(Layer("st", f"output_blocks.{oidx}.{j}", ch, ch, cfg.num_heads, ch // cfg.num_heads))
+                j += 1
+            out_ds = ds
+            if level and i == cfg.num_res_blocks:
+                blk.layers.append(Layer("up", f"output_blocks.{oidx}.{j}", ch, ch))
+                out_ds = ds // 2
+            blk.out_ch, blk.out_ds = ch, out_ds
+            blocks.append(blk)
+            ds = out_ds
+            oidx += 1
+    return blocks
+
+
+# ----------------------------------------------------------------------------------------------
+# Parameter inventory (state-dict keys and shapes)
+# ----------------------------------------------------------------------------------------------
+def _attn_params(p: "OrderedDict[str, tuple]", prefix: str, qdim: int, kdim: int) -> None:
+    p[f"{prefix}.to_q.weight"] = (qdim, qdim)
+    p[f"{prefix}.to_k.weight"] = (qdim, kdim)
+    p[f"{prefix}.to_v.weight"] = (qdim, kdim)
+    p[f"{prefix}.to_out.0.weight"] = (qdim, qdim)
+    p[f"{prefix}.to_out.0.bias"] = (qdim,)
+
+
+def _ff_params(p, prefix: str, dim: int) -> None:
+    p[f"{prefix}.net.0.proj.weight"] = (dim * 8, dim)
+    p[f"{prefix}.net.0.proj.bias"] = (dim * 8,)
+    p[f"{prefix}.net.2.weight"] = (dim, dim * 4)
+    p[f"{prefix}.net.2.bias"] = (dim,)
+
+
+def _norm_params(p, prefix: str, dim: int) -> None:
+    p[f"{prefix}.weight"] = (dim,)
+    p[f"{prefix}.bias"] = (dim,)
+
+
+def _mlp3(p, prefix: str, din: int, hidden: int, dout: int) -> None:
+    for i, (a, b) in zip((0, 2, 4), ((din, hidden), (hidden, hidden), (hidden, dout))):
+        p[f"{prefix}.{i}.weight"] = (b, a)
+        p[f"{prefix}.{i}.bias"] = (b,)
+
+
+def unet_param_shapes(cfg: UNetConfig) -> "OrderedDict[str, tuple]":
+    """All parameters of UNetModel in registration order (matches reference state_dict() order)."""
+    p: "OrderedDict[str, tuple]" = OrderedDict()
+    mc, ted = cfg.model_channels, cfg.time_embed_dim
+    p["time_embed.0.weight"] = (ted, mc)
+    p["time_embed.0.bias"] = (ted,)
+    p["time_embed.2.weight"] = (ted, ted)
+    p["time_embed.2.bias"] = (ted,)
+
+    def res(prefix, cin, cout):
+        _norm_params(p, f"{prefix}.in_layers.0", cin)
+        p[f"{prefix}.in_layers.2.weight"] = (cout, cin, 3, 3)
+        p[f"{prefix}.in_layers.2.bias"] = (cout,)
+        p[f"{prefix}.emb_layers.1.weight"] = (cout, ted)
+        p[f"{prefix}.emb_layers.1.bias"] = (cout,)
+        _norm_params(p, f"{prefix}.out_layers.0", cout)
+        p[f"{prefix}.out_layers.3.weight"] = (cout, cout, 3, 3)
+        p[f"{prefix}.out_layers.3.bias"] = (cout,)
+        if cin != cout:
+            p[f"{prefix}.skip_connection.weight"] = (cout, cin, 1, 1)
+            p[f"{prefix}.skip_connection.bias"] = (cout,)
+
+    def st(prefix, c):
+        _norm_params(p, f"{prefix}.norm", c)
+        p[f"{prefix}.proj_in.weight"] = (c, c, 1, 1)
+        p[f"{prefix}.proj_in.bias"] = (c,)
+        for d in range(cfg.transformer_depth):
+            tb = f"{prefix}.transformer_blocks.{d}"
+            _attn_params(p, f"{tb}.attn1", c, c)
+            _ff_params(p, f"{tb}.ff", c)
+            _attn_params(p, f"{tb}.attn2", c, cfg.context_dim)
+            _norm_params(p, f"{tb}.norm1", c)
+            _norm_params(p, f"{tb}.norm2", c)
+            _norm_params(p, f"{tb}.norm3", c)
+            fu = f"{tb}.fuser"
+            p[f"{fu}.alpha_attn"] = ()
+            p[f"{fu}.alpha_dense"] = ()
+            p[f"{fu}.linear.weight"] = (c, cfg.context_dim)
+            p[f"{fu}.linear.bias"] = (c,)
+            _attn_params(p, f"{fu}.attn", c, c)
+            _ff_params(p, f"{fu}.ff", c)
+            _norm_params(p, f"{fu}.norm1", c)
+            _norm_params(p, f"{fu}.norm2", c)
+        p[f"{prefix}.proj_out.weight"] = (c, c, 1, 1)
+        p[f"{prefix}.proj_out.bias"] = (c,)
+
+    for blk in block_schedule(cfg):
+        for ly in blk.layers:
+            if ly.kind == "conv_in":
+                p[f"{ly.prefix}.weight"] = (ly.cout, ly.cin, 3, 3)
+                p[f"{ly.prefix}.bias"] = (ly.cout,)
+            elif ly.kind == "res":
+                res(ly.prefix, ly.cin, ly.cout)
+            elif ly.kind == "st":
+                st(ly.prefix, ly.cin)
+            elif ly.kind == "down":
+                p[f"{ly.prefix}.op.weight"] = (ly.cout, ly.cin, 3, 3)
+                p[f"{ly.prefix}.op.bias"] = (ly.cout,)
+            elif ly.kind == "up":
+                p[f"{ly.prefix}.conv.weight"] = (ly.cout, ly.cin, 3, 3)
+                p[f"{ly.prefix}.conv.bias"] = (ly.cout,)
+    _norm_params(p, "out.0", mc)
+    p["out.2.weight"] = (cfg.out_channels, mc, 3, 3)
+    p["out.2.bias"] = (cfg.out_channels,)
+
+    pn = "position_net"
+    din = cfg.tok_feat_dim + cfg.position_dim
+    if cfg.tokenizer == "text":
+        p[f"{pn}.null_positive_feature"] = (cfg.tok_in_dim,)
+        p[f"{pn}.null_position_feature"] = (cfg.position_dim,)
+        _mlp3(p, f"{pn}.linears", din, cfg.tok_hidden, cfg.tok_out_dim)
+    elif cfg.tokenizer == "text_image":
+        p[f"{pn}.null_text_feature"] = (cfg.tok_in_dim,)
+        p[f"{pn}.null_image_feature"] = (cfg.tok_in_dim,)
+        p[f"{pn}.null_position_feature"] = (cfg.position_dim,)
+        _mlp3(p, f"{pn}.linears_text", din, cfg.tok_hidden, cfg.tok_out_dim)
+        _mlp3(p, f"{pn}.linears_image", din, cfg.tok_hidden, cfg.tok_out_dim)
+    elif cfg.tokenizer == "keypoint":
+        p[f"{pn}.person_embeddings"] = (cfg.max_persons, cfg.tok_out_dim)
+        p[f"{pn}.keypoint_embeddings"] = (17, cfg.tok_out_dim)
+        p[f"{pn}.null_person_feature"] = (cfg.tok_out_dim,)
+        p[f"{pn}.null_xy_feature"] = (cfg.position_dim,)
+        _mlp3(p, f"{pn}.linears", din, cfg.tok_hidden, cfg.tok_out_dim)
+    else:
+        raise ValueError(f"unknown tokenizer {cfg.tokenizer!r}")
+    return p
+
+
+def synthetic_state_dict(cfg: UNetConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Seeded fp32 CPU weights with NO all-zero tensors.
+
+    The reference zero-initialises 253 tensors (zero_module on proj_out / out_layers.3 / out.2 and
+    alpha_attn/alpha_dense) which would make eps == 0 and hide every bug; here every
+    tensor is drawn so that activations stay O(1): weights ~ N(0, 1/fan_in), norm scales ~ 1 + 0.1 N,
+    biases ~ 0.05 N, alphas ~ U(-1, 1).  The draw order is the registration order, one generator,
+    so the same bits are produced on every box with this torch build.
+    """
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = OrderedDict()
+    for key, shape in unet_param_shapes(cfg).items():
+        leaf = key.rsplit(".", 1)[-1]
+        if leaf in ("alpha_attn", "alpha_dense"):
+            t = torch.rand((), generator=g) * 2 - 1
+        elif leaf == "bias" or key.startswith("position_net.null_"):
+            t = torch.randn(shape, generator=g) * 0.05
+        elif len(shape) == 1:                                   # norm scales
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        elif key.endswith("_embeddings"):
+            t = torch.randn(shape, generator=g)
+        else:
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            t = torch.randn(shape, generator=g) * (fan_in ** -0.5)
+        sd[key] = t
+    return sd
+
+
+def flops_per_forward(cfg: UNetConfig, G: int, fuser_on: bool = True) -> float:
+    """Algorithmic 2*MAC of one UNet forward for ONE sample (SURVEY 8d analytic generator)."""
+    ctx, ted = cfg.context_dim, cfg.time_embed_dim
+    total = 0.0
+    for blk in block_schedule(cfg):
+        hw = (cfg.image_size // blk.ds) ** 2
+        for ly in blk.layers:
+            if ly.kind == "conv_in":
+                total += 18.0 * hw * ly.cin * ly.cout
+            elif ly.kind == "res":
+                total += 18.0 * hw * ly.cin * ly.cout + 18.0 * hw * ly.cout ** 2 + 2.0 * ted * ly.cout
+                if ly.cin != ly.cout:
+                    total += 2.0 * hw * ly.cin * ly.cout
+            elif ly.kind == "st":
+                C, T = ly.cin, hw
+                total += 4.0 * T * C * C                                   # proj in/out
+                total += 8.0 * T * C * C + 4.0 * T * T * C                 # attn1
+                if fuser_on:
+                    total += 2.0 * G * ctx * C + 8.0 * (T + G) * C * C + 4.0 * (T + G) ** 2 * C + 24.0 * T * C * C
+                total += 4.0 * T * C * C + 4.0 * 77 * ctx * C + 4.0 * T * 77 * C   # attn2
+                total += 24.0 * T * C * C                                  # ff
+            elif ly.kind == "down":
+                total += 18.0 * (hw // 4) * ly.cin * ly.cout
+            elif ly.kind == "up":
+                total += 18.0 * (hw * 4) * ly.cin * ly.cout
+    total += 18.0 * cfg.image_size ** 2 * cfg.model_channels * cfg.out_channels
+    total += 2.0 * (cfg.model_channels * ted + ted * ted)
+    din = cfg.tok_feat_dim + cfg.position_dim
+    n_mlp = 2 if cfg.tokenizer == "text_image" else 1
+    gtok = G // n_mlp
+    total += n_mlp * 2.0 * gtok * (din * cfg.tok_hidden + cfg.tok_hidden ** 2 + cfg.tok_hidden * cfg.tok_out_dim)
+    return total

@@ -1,0 +1,145 @@
+/* gligen_b200 C ABI  --  libgligen_b200.so
+ *
+ * Drop-in boundary for the GLIGEN per-timestep denoiser.  The reference is pure
+ * Python/PyTorch and has no FFI of its own; each entry point below replaces the torch library call(s)
+ * the reference makes at the cited file:line (paths relative to the reference checkout).  Signatures
+ * are plain C: device pointers, sizes, a cudaStream_t passed as void*.  No torch types cross the ABI.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; glg_last_error() returns a thread-local message.
+ *   - all work is enqueued on `stream`; nothing synchronises the device; every call is CUDA-graph
+ *     capture safe (no allocation, no host sync) once the tensor-map cache is warm (first call per
+ *     distinct (pointer, shape) creates a CUtensorMap on the host - also capture safe).
+ *   - activations are bf16, channels-last: [B, H*W, C] == [B*T, C] row-major with an explicit leading
+ *     dimension (ld, in elements) so that channel-concatenated buffers are addressed in place.
+ *   - weights are bf16 [N, K] row-major (nn.Linear layout); 3x3 conv weights are packed [9][Cout][Cin].
+ *   - statistics, biases, gates and sampler state are fp32.
+ */
+#ifndef GLIGEN_B200_H_
+#define GLIGEN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLG_ABI_VERSION 1
+
+#define GLG_ACT_NONE 0
+#define GLG_ACT_SILU 1
+
+/* ---- library ------------------------------------------------------------------------------- */
+int glg_abi_version(void);
+const char* glg_last_error(void);
+/* number of kernels launched by this library since load / since the last reset (bench gpu_launches). */
+int64_t glg_launch_count(void);
+void glg_reset_launch_count(void);
+
+/* ---- tensor-core GEMM / implicit-GEMM convolution -------------------------------------------
+ * out[M,N] = epilogue( A[M,K] * W[N,K]^T )      tcgen05.mma (bf16 x bf16 -> fp32 in TMEM), TMA-fed.
+ *
+ * Replaces: nn.Linear (attention.py:110-115,161-165,42,61,239), nn.Conv2d 1x1 (attention.py:349,360;
+ * openaimodel.py:194), nn.Conv2d 3x3 stride 1 (openaimodel.py:157,183,70; conv_mode=1), the
+ * PositionNet / time-embed MLPs (text_grounding_net.py:18-24, openaimodel.py:282-286,171-177).
+ *
+ * epilogue, in this order:  v = acc + bias[n] + rowbias[row / rows_per_batch][n];
+ *                           v = act(v);   v *= *gate;   v += residual[row][n];
+ * geglu=1 (attention.py:42-44): W/bias rows are packed per 256-row tile as [128 x-rows | 128 gate-rows]
+ *   and out[M, N/2] = (x + bx) * gelu_erf(g + bg); act/gate/residual are not applied.
+ * conv_mode=1: A is an NHWC activation [B, H, W, C=K] (ld = pixel stride); W is [9][N][K]; zero padding 1.
+ */
+typedef struct GlgGemmArgs {
+  const void* A;          /* bf16 */
+  int64_t lda;            /* elements between consecutive rows (pixels) of A */
+  const void* W;          /* bf16 [N(*9), K] row-major, contiguous */
+  void* out;              /* bf16 (or fp32 if out_fp32) */
+  int64_t ldc;
+  int32_t M, N, K;
+  int32_t out_fp32;
+  const float* bias;      /* [N] or NULL */
+  const float* rowbias;   /* [M / rows_per_batch, ld_rowbias] fp32 or NULL (ResBlock emb add, openaimodel.py:221-230) */
+  int64_t ld_rowbias;
+  int32_t rows_per_batch;
+  int32_t act;            /* GLG_ACT_* */
+  const float* gate;      /* device scalar (scale * tanh(alpha), attention.py:241-242) or NULL */
+  const void* residual;   /* bf16 [M, ldr] or NULL */
+  int64_t ldr;
+  int32_t geglu;
+  int32_t conv_mode;      /* 0 = plain GEMM, 1 = 3x3 stride-1 pad-1 convolution */
+  int32_t H, Wd, Bn;      /* conv_mode: spatial dims and batch; M == Bn*H*Wd */
+} GlgGemmArgs;
+int glg_gemm(const GlgGemmArgs* args, void* stream);
+
+/* ---- fused attention --------------------------------------------------------------------------
+ * O[b, i, h*d:(h+1)*d] = softmax_j( Q[b,i,h,:] . K[b,j,h,:] * d^-1/2 ) V[b,j,h,:]      (flash style, online
+ * softmax in fp32, scores never leave the SM).  Replaces the two einsums + softmax of
+ * attention.py:142-146 (CrossAttention) and :180-183 (SelfAttention; also GatedSelfAttentionDense's
+ * attention over [visual ; grounding] tokens with only the first Lq query rows kept, :241).
+ * q/k/v are bf16 with independent row strides (elements) and batch strides so that packed QKV / KV
+ * GEMM outputs are consumed in place.  d_head in {8,16,...,160}, multiple of 8.
+ */
+typedef struct GlgAttnArgs {
+  const void* q; const void* k; const void* v; void* out;   /* bf16 */
+  int64_t q_row, k_row, v_row, o_row;        /* row strides (elements) */
+  int64_t q_batch, k_batch, v_batch, o_batch;/* batch strides (elements) */
+  int32_t B, heads, d_head, Lq, Lk;
+  float scale;                               /* d_head^-0.5 */
+} GlgAttnArgs;
+int glg_attention(const GlgAttnArgs* args, void* stream);
+
+/* ---- normalisation ---------------------------------------------------------------------------
+ * GroupNorm over channels-last input (32 groups in the reference): fp32 statistics, affine, optional
+ * SiLU, bf16 out.  Replaces GroupNorm32+SiLU (util.py:208-226, openaimodel.py:155-156,179-180,392-393;
+ * eps 1e-5) and Normalize (attention.py:76-77; eps 1e-6, no SiLU).  `stats` is a caller-provided fp32
+ * scratch of B*groups*2 floats.
+ */
+int glg_groupnorm(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma, const float* beta,
+                  float* stats, int32_t B, int32_t HW, int32_t C, int32_t groups, float eps, int32_t silu,
+                  void* stream);
+/* LayerNorm over the last dim C (attention.py:309-311,225-226; eps 1e-5).  Row r of batch b is read at
+ * x + b*x_batch + r*C and written at y + b*y_batch + r*C (lets the fuser build LN(cat[x, objs]) in place). */
+int glg_layernorm(const void* x, int64_t x_batch, void* y, int64_t y_batch, const float* gamma, const float* beta,
+                  int32_t B, int32_t rows, int32_t C, float eps, void* stream);
+
+/* ---- data movement / small ops ------------------------------------------------------------- */
+/* First conv: NCHW fp32 x (+ optional extra channels, inpainting openaimodel.py:444-447) -> NHWC bf16.
+ * w fp32 packed [9][Cin][Cout] (tap-major), Cin = C0 + C1.  openaimodel.py:305,454. */
+int glg_conv_in(const float* x, int32_t C0, const float* extra, int32_t C1, const float* w, const float* bias,
+                void* out, int64_t ldo, int32_t B, int32_t H, int32_t Wd, int32_t Cout, void* stream);
+/* Last conv: NHWC bf16 (already GN+SiLU'd) -> NCHW fp32 eps.  w fp32 packed [9][Cout][Cin], Cout in {4, 8}.  openaimodel.py:391-395. */
+int glg_conv_out(const void* x, int64_t ldx, const float* w, const float* bias, float* out,
+                 int32_t B, int32_t H, int32_t Wd, int32_t Cin, int32_t Cout, void* stream);
+/* nearest 2x upsample, NHWC bf16 (openaimodel.py:79 F.interpolate). */
+int glg_upsample2x(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t B, int32_t H, int32_t Wd, int32_t C, void* stream);
+/* im2col for the 3x3 stride-2 pad-1 downsample conv (openaimodel.py:104-106): y[B*Ho*Wo, 9*C], k = tap*C + c. */
+int glg_im2col_s2(const void* x, int64_t ldx, void* y, int32_t B, int32_t H, int32_t Wd, int32_t C, void* stream);
+/* strided 2-D copy of bf16 rows: y[r, 0:C] = x[r, 0:C] (used to place skip tensors; C % 8 == 0). */
+int glg_copy_rows(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int32_t C, void* stream);
+/* timestep_embedding (util.py:160-180): out bf16 [B, dim] = [cos(t f) | sin(t f)], f_k = exp(-ln(1e4) k / (dim/2)). */
+int glg_timestep_embedding(const int64_t* t, void* out, int32_t B, int32_t dim, void* stream);
+/* PositionNet input rows (text_grounding_net.py:33-45, text_image_grounding_net.py:44-60,
+ * keypoint_grounding_net.py:38-55): out bf16 [B*N, F + P] = [feat*m_f + (1-m_f)*null_f | fourier(coords)*m + (1-m)*null_p]
+ * feat: fp32 [B, N, F] (feat_batch_stride = 0 broadcasts one [N, F] table over the batch); coords fp32 [B, N, ncoord];
+ * P = freqs*2*ncoord laid out per frequency as [sin(f*coords) | cos(f*coords)] (util.py:20-26);
+ * rows have stride ldo >= F + P and columns [F+P, ldo) are zero (pads K to a multiple of 64 for glg_gemm). */
+int glg_position_features(const float* feat, int64_t feat_batch_stride, const float* feat_mask, const float* null_feat,
+                          const float* coords, const float* pos_mask, const float* null_pos, void* out, int64_t ldo,
+                          int32_t B, int32_t N, int32_t F, int32_t ncoord, int32_t freqs, void* stream);
+/* fp32 -> bf16 cast of a contiguous buffer (context / weights staging). */
+int glg_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
+
+/* ---- sampler update (plms.py:121-158, ddim.py:113-134), one fused fp32 kernel ---------------
+ * e      = e_u + g*(e_c - e_u)                       (if e_uncond != NULL, else e = e_cond)
+ * e'     = c0*e + c1*old1 + c2*old2 + c3*old3        (Adams-Bashforth / identity / improved Euler)
+ * x_prev = sqrt(a_prev) * (x - sqrt(1-a_t) e')/sqrt(a_t) + sqrt(1-a_prev) * e'        (sigma = 0)
+ * e_out (nullable) receives e (the CFG-combined epsilon, kept for the multistep history). */
+int glg_sampler_update(const float* x, const float* e_cond, const float* e_uncond, float guidance,
+                       const float* old1, const float* old2, const float* old3,
+                       float c0, float c1, float c2, float c3,
+                       float a_t, float a_prev, float* e_out, float* x_prev, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLIGEN_B200_H_ */
