@@ -1,0 +1,546 @@
+"""The denoising engine: weight packing, static workspace, and the per-timestep UNet forward expressed as
+a flat list of kernel launches (a "plan") that is replayed - directly or as a CUDA graph - every step.
+
+Mirrors UNetModel.forward (reference ldm/modules/diffusionmodules/openaimodel.py:420-464) with these
+B200-first restructurings, all exact in real arithmetic:
+  * channels-last bf16 activations; [B,C,H,W] <-> [B,(HW),C] rearranges of SpatialTransformer
+    (attention.py:371,374) disappear;
+  * skip connections are written by their producer straight into the channel slice of the concat buffer
+    of the output block that will consume them (no torch.cat, openaimodel.py:461);
+  * Q/K/V projections fused into one GEMM, GEGLU fused into the FF1 epilogue, bias / time-embedding /
+    residual / tanh-gate adds fused into GEMM epilogues, the 22 ResBlock emb projections in one GEMM;
+  * cond and uncond passes of classifier-free guidance can run as one 2B batch;
+  * the gated self-attention fuser is skipped when scale == 0 (x + 0*f(x), attention.py:241-242).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from .spec import UNetConfig, block_schedule
+
+ACT_NONE, ACT_SILU = 0, 1
+
+
+def _rup(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class Plan:
+    """Static buffers + ordered launch list for one (batch rows, grounding tokens) shape."""
+
+    def __init__(self):
+        self.steps: List[Tuple[str, bool, Callable[[], None]]] = []   # (name, fuser_only, fn)
+        self.inp: Dict[str, torch.Tensor] = {}
+        self.out: Optional[torch.Tensor] = None
+        self.graphs: Dict[bool, object] = {}
+        self.warm: Dict[bool, int] = {}
+
+    def add(self, name: str, fn: Callable[[], None], fuser: bool = False) -> None:
+        self.steps.append((name, fuser, fn))
+
+    def run(self, fuser_on: bool) -> None:
+        for _, fuser, fn in self.steps:
+            if fuser and not fuser_on:
+                continue
+            fn()
+
+
+class Engine:
+    def __init__(self, cfg: UNetConfig, ops, use_graphs: bool = True):
+        self.cfg = cfg
+        self.ops = ops
+        self.dev = ops.device
+        self.adt = ops.act_dtype
+        self.blocks = block_schedule(cfg)
+        self.W: Dict[str, torch.Tensor] = {}
+        self.plans: Dict[Tuple[int, int, int], Plan] = {}
+        self.scale = 1.0
+        self.use_graphs = use_graphs and self.dev.type == "cuda"
+        self.loaded = False
+        # (prefix of every SpatialTransformer, in execution order) -> index into the gate table
+        self.st_prefixes = [ly.prefix for blk in self.blocks for ly in blk.layers if ly.kind == "st"]
+        self.res_layers = [ly for blk in self.blocks for ly in blk.layers if ly.kind == "res"]
+        self.emb_off: Dict[str, int] = {}
+        off = 0
+        for ly in self.res_layers:
+            self.emb_off[ly.prefix] = off
+            off += ly.cout
+        self.emb_total = off
+        self.n_streams = 2 if cfg.tokenizer == "text_image" else 1
+        self.pos_k = _rup(cfg.tok_feat_dim + cfg.position_dim, 64)
+
+    # ------------------------------------------------------------------------------------------
+    # weights
+    # ------------------------------------------------------------------------------------------
+    def _a(self, t: torch.Tensor) -> torch.Tensor:
+        return t.detach().to(device=self.dev, dtype=self.adt).contiguous()
+
+    def _f(self, t: torch.Tensor) -> torch.Tensor:
+        return t.detach().to(device=self.dev, dtype=torch.float32).contiguous()
+
+    @staticmethod
+    def _pack_geglu(w: torch.Tensor, b: torch.Tensor):
+        """[x rows | gate rows] -> per 256-row tile [128 x | 128 gate] (glg_gemm geglu layout)."""
+        n2 = w.shape[0] // 2
+        assert n2 % 128 == 0, "GEGLU inner dim must be a multiple of 128"
+        wx, wg = w[:n2].reshape(n2 // 128, 128, -1), w[n2:].reshape(n2 // 128, 128, -1)
+        bx, bg = b[:n2].reshape(n2 // 128, 128), b[n2:].reshape(n2 // 128, 128)
+        return torch.stack([wx, wg], dim=1).reshape(2 * n2, -1), torch.stack([bx, bg], dim=1).reshape(2 * n2)
+
+    @staticmethod
+    def _pack_conv3(w: torch.Tensor) -> torch.Tensor:
+        """[Cout, Cin, 3, 3] -> [9*Cout, Cin] (tap-major)."""
+        co, ci = w.shape[:2]
+        return w.permute(2, 3, 0, 1).reshape(9 * co, ci)
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        cfg, W = self.cfg, self.W
+        W.clear()
+        W["time_embed.0.w"], W["time_embed.0.b"] = self._a(sd["time_embed.0.weight"]), self._f(sd["time_embed.0.bias"])
+        W["time_embed.2.w"], W["time_embed.2.b"] = self._a(sd["time_embed.2.weight"]), self._f(sd["time_embed.2.bias"])
+        W["emb_all.w"] = self._a(torch.cat([sd[f"{ly.prefix}.emb_layers.1.weight"] for ly in self.res_layers], dim=0))
+        W["emb_all.b"] = self._f(torch.cat([sd[f"{ly.prefix}.emb_layers.1.bias"] for ly in self.res_layers], dim=0))
+        self.set_first_conv(sd["input_blocks.0.0.weight"], sd["input_blocks.0.0.bias"])
+        for blk in self.blocks:
+            for ly in blk.layers:
+                p = ly.prefix
+                if ly.kind == "res":
+                    W[f"{p}.gn1.g"], W[f"{p}.gn1.b"] = self._f(sd[f"{p}.in_layers.0.weight"]), self._f(sd[f"{p}.in_layers.0.bias"])
+                    W[f"{p}.conv1.w"] = self._a(self._pack_conv3(sd[f"{p}.in_layers.2.weight"]))
+                    W[f"{p}.conv1.b"] = self._f(sd[f"{p}.in_layers.2.bias"])
+                    W[f"{p}.gn2.g"], W[f"{p}.gn2.b"] = self._f(sd[f"{p}.out_layers.0.weight"]), self._f(sd[f"{p}.out_layers.0.bias"])
+                    W[f"{p}.conv2.w"] = self._a(self._pack_conv3(sd[f"{p}.out_layers.3.weight"]))
+                    W[f"{p}.conv2.b"] = self._f(sd[f"{p}.out_layers.3.bias"])
+                    if ly.cin != ly.cout:
+                        W[f"{p}.skip.w"] = self._a(sd[f"{p}.skip_connection.weight"].reshape(ly.cout, ly.cin))
+                        W[f"{p}.skip.b"] = self._f(sd[f"{p}.skip_connection.bias"])
+                elif ly.kind == "down":
+                    w = sd[f"{p}.op.weight"]
+                    W[f"{p}.w"] = self._a(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1))      # [Cout, 9*Cin], k = tap*Cin + c
+                    W[f"{p}.b"] = self._f(sd[f"{p}.op.bias"])
+                elif ly.kind == "up":
+                    W[f"{p}.w"] = self._a(self._pack_conv3(sd[f"{p}.conv.weight"]))
+                    W[f"{p}.b"] = self._f(sd[f"{p}.conv.bias"])
+                elif ly.kind == "st":
+                    C = ly.cin
+                    W[f"{p}.gn.g"], W[f"{p}.gn.b"] = self._f(sd[f"{p}.norm.weight"]), self._f(sd[f"{p}.norm.bias"])
+                    W[f"{p}.proj_in.w"], W[f"{p}.proj_in.b"] = self._a(sd[f"{p}.proj_in.weight"].reshape(C, C)), self._f(sd[f"{p}.proj_in.bias"])
+                    W[f"{p}.proj_out.w"], W[f"{p}.proj_out.b"] = self._a(sd[f"{p}.proj_out.weight"].reshape(C, C)), self._f(sd[f"{p}.proj_out.bias"])
+                    tb = f"{p}.transformer_blocks.0"
+                    for a in ("attn1", "fuser.attn"):
+                        W[f"{tb}.{a}.qkv.w"] = self._a(torch.cat([sd[f"{tb}.{a}.to_q.weight"], sd[f"{tb}.{a}.to_k.weight"], sd[f"{tb}.{a}.to_v.weight"]], dim=0))
+                        W[f"{tb}.{a}.out.w"], W[f"{tb}.{a}.out.b"] = self._a(sd[f"{tb}.{a}.to_out.0.weight"]), self._f(sd[f"{tb}.{a}.to_out.0.bias"])
+                    W[f"{tb}.attn2.q.w"] = self._a(sd[f"{tb}.attn2.to_q.weight"])
+                    W[f"{tb}.attn2.kv.w"] = self._a(torch.cat([sd[f"{tb}.attn2.to_k.weight"], sd[f"{tb}.attn2.to_v.weight"]], dim=0))
+                    W[f"{tb}.attn2.out.w"], W[f"{tb}.attn2.out.b"] = self._a(sd[f"{tb}.attn2.to_out.0.weight"]), self._f(sd[f"{tb}.attn2.to_out.0.bias"])
+                    for f in ("ff", "fuser.ff"):
+                        w1, b1 = self._pack_geglu(sd[f"{tb}.{f}.net.0.proj.weight"].float(), sd[f"{tb}.{f}.net.0.proj.bias"].float())
+                        W[f"{tb}.{f}.w1"], W[f"{tb}.{f}.b1"] = self._a(w1), self._f(b1)
+                        W[f"{tb}.{f}.w2"], W[f"{tb}.{f}.b2"] = self._a(sd[f"{tb}.{f}.net.2.weight"]), self._f(sd[f"{tb}.{f}.net.2.bias"])
+                    for n in ("norm1", "norm2", "norm3", "fuser.norm1", "fuser.norm2"):
+                        W[f"{tb}.{n}.g"], W[f"{tb}.{n}.b"] = self._f(sd[f"{tb}.{n}.weight"]), self._f(sd[f"{tb}.{n}.bias"])
+                    W[f"{tb}.fuser.linear.w"], W[f"{tb}.fuser.linear.b"] = self._a(sd[f"{tb}.fuser.linear.weight"]), self._f(sd[f"{tb}.fuser.linear.bias"])
+        W["out.gn.g"], W["out.gn.b"] = self._f(sd["out.0.weight"]), self._f(sd["out.0.bias"])
+        W["out.w"] = self._f(sd["out.2.weight"].permute(2, 3, 0, 1).reshape(9, cfg.out_channels, cfg.model_channels))
+        W["out.b"] = self._f(sd["out.2.bias"])
+        # fuser gates: alpha table [n_st, 2] (attn, dense); gates = scale * tanh(alpha)
+        alphas = torch.stack([torch.stack([sd[f"{p}.transformer_blocks.0.fuser.alpha_attn"].reshape(()),
+                                           sd[f"{p}.transformer_blocks.0.fuser.alpha_dense"].reshape(())]) for p in self.st_prefixes])
+        W["alphas"] = self._f(alphas)
+        W["gates"] = torch.zeros_like(W["alphas"])
+        self._pack_position_net(sd)
+        self.loaded = True
+        self.set_scale(self.scale)
+
+    def _pack_position_net(self, sd) -> None:
+        cfg, W, pn = self.cfg, self.W, "position_net"
+
+        def mlp(src: str, dst: str):
+            w0 = sd[f"{pn}.{src}.0.weight"].float()
+            w0p = torch.zeros(w0.shape[0], self.pos_k)
+            w0p[:, : w0.shape[1]] = w0
+            W[f"{dst}.0.w"], W[f"{dst}.0.b"] = self._a(w0p), self._f(sd[f"{pn}.{src}.0.bias"])
+            W[f"{dst}.2.w"], W[f"{dst}.2.b"] = self._a(sd[f"{pn}.{src}.2.weight"]), self._f(sd[f"{pn}.{src}.2.bias"])
+            W[f"{dst}.4.w"], W[f"{dst}.4.b"] = self._a(sd[f"{pn}.{src}.4.weight"]), self._f(sd[f"{pn}.{src}.4.bias"])
+
+        if cfg.tokenizer == "text":
+            mlp("linears", "pn.s0")
+            W["pn.s0.null_feat"] = self._f(sd[f"{pn}.null_positive_feature"])
+            W["pn.null_pos"] = self._f(sd[f"{pn}.null_position_feature"])
+        elif cfg.tokenizer == "text_image":
+            mlp("linears_text", "pn.s0")
+            mlp("linears_image", "pn.s1")
+            W["pn.s0.null_feat"] = self._f(sd[f"{pn}.null_text_feature"])
+            W["pn.s1.null_feat"] = self._f(sd[f"{pn}.null_image_feature"])
+            W["pn.null_pos"] = self._f(sd[f"{pn}.null_position_feature"])
+        else:  # keypoint: person x keypoint embedding table is input independent (keypoint_grounding_net.py:39-42)
+            mlp("linears", "pn.s0")
+            P = cfg.max_persons
+            pe = sd[f"{pn}.person_embeddings"].float().unsqueeze(1).repeat(1, 17, 1).reshape(P * 17, -1)
+            ke = torch.cat([sd[f"{pn}.keypoint_embeddings"].float()] * P, dim=0)
+            W["pn.table"] = self._f(pe + ke)
+            W["pn.s0.null_feat"] = self._f(sd[f"{pn}.null_person_feature"])
+            W["pn.null_pos"] = self._f(sd[f"{pn}.null_xy_feature"])
+
+    def set_first_conv(self, weight: torch.Tensor, bias: torch.Tensor) -> None:
+        """openaimodel.py:400-413 swaps input_blocks[0][0]; here: repack into the static weight slot."""
+        w = self._f(weight.float().permute(2, 3, 1, 0).reshape(9, weight.shape[1], weight.shape[0]))   # [9][Cin][Cout]
+        b = self._f(bias)
+        if "conv_in.w" in self.W and self.W["conv_in.w"].shape == w.shape:
+            self.W["conv_in.w"].copy_(w)          # in place: captured graphs keep pointing at this storage
+            self.W["conv_in.b"].copy_(b)
+        else:
+            self.W["conv_in.w"], self.W["conv_in.b"] = w, b
+            self.plans.clear()
+
+    def set_scale(self, scale) -> None:
+        """GatedSelfAttentionDense.scale: one float for every fuser (set_alpha_scale, gligen_inference.py:24-28)
+        or one value per SpatialTransformer in execution order."""
+        if isinstance(scale, (int, float)):
+            scale = [float(scale)] * len(self.st_prefixes)
+        scale = [float(s) for s in scale]
+        assert len(scale) == len(self.st_prefixes)
+        self.scales = scale
+        self.scale = max(abs(s) for s in scale) if scale else 0.0     # 0 <=> every fuser is off
+        if self.loaded:
+            sv = torch.tensor(scale, dtype=torch.float32).view(-1, 1).to(self.dev)
+            self.W["gates"].copy_(torch.tanh(self.W["alphas"]) * sv)
+
+    # ------------------------------------------------------------------------------------------
+    # plan construction
+    # ------------------------------------------------------------------------------------------
+    def _buf(self, numel: int, dtype=None) -> torch.Tensor:
+        return torch.empty(max(int(numel), 8), device=self.dev, dtype=dtype or self.adt)
+
+    def _sizes(self, Bt: int, N: int, nctx: int) -> Dict[str, int]:
+        cfg = self.cfg
+        G = N * self.n_streams
+        s = dict(t0=0, sb=0, sc=0, sd=0, up=0, col=0, xs=0, qkv=0, ao=0, ffh=0, ln=0, objp=0, kv=0, blk=0)
+        for blk in self.blocks:
+            hw = (cfg.image_size // blk.ds) ** 2
+            for ly in blk.layers:
+                if ly.kind == "res":
+                    s["t0"] = max(s["t0"], Bt * hw * ly.cin)
+                    for k in ("sb", "sc", "sd", "blk"):
+                        s[k] = max(s[k], Bt * hw * ly.cout)
+                elif ly.kind == "st":
+                    C, T = ly.cin, hw
+                    s["t0"] = max(s["t0"], Bt * T * C)
+                    s["xs"] = max(s["xs"], Bt * T * C)
+                    s["ao"] = max(s["ao"], Bt * T * C)
+                    s["qkv"] = max(s["qkv"], Bt * (T + G) * 3 * C)
+                    s["ln"] = max(s["ln"], Bt * (T + G) * C)
+                    s["ffh"] = max(s["ffh"], Bt * T * 4 * C)
+                    s["objp"] = max(s["objp"], Bt * G * C)
+                    s["kv"] = max(s["kv"], Bt * nctx * 2 * C)
+                    s["blk"] = max(s["blk"], Bt * T * C)
+                elif ly.kind == "down":
+                    s["col"] = max(s["col"], Bt * (hw // 4) * 9 * ly.cin)
+                elif ly.kind == "up":
+                    s["up"] = max(s["up"], Bt * hw * 4 * ly.cin)
+        return s
+
+    def _build_plan(self, Bt: int, N: int, nctx: int) -> Plan:
+        cfg, ops, W = self.cfg, self.ops, self.W
+        S = self.n_streams
+        G = N * S
+        P = Plan()
+        sz = self._sizes(Bt, N, nctx)
+        B_ = {k: self._buf(v) for k, v in sz.items()}
+        B_["blk2"] = self._buf(sz["blk"])
+        stats = self._buf(Bt * 32 * 2, torch.float32)
+        Himg = cfg.image_size
+        f32 = torch.float32
+
+        def view(name, *shape):
+            n = 1
+            for d in shape:
+                n *= d
+            return B_[name][:n].view(*shape)
+
+        # ---- static inputs -------------------------------------------------------------------
+        P.inp["x"] = torch.zeros(Bt, cfg.in_channels, Himg, Himg, device=self.dev, dtype=f32)
+        if cfg.inpaint_mode:
+            P.inp["extra"] = torch.zeros(Bt, cfg.in_channels + 1, Himg, Himg, device=self.dev, dtype=f32)
+        P.inp["t"] = torch.zeros(Bt, device=self.dev, dtype=torch.int64)
+        P.inp["context"] = torch.zeros(Bt, nctx, cfg.context_dim, device=self.dev, dtype=f32)
+        if cfg.tokenizer == "keypoint":
+            P.inp["coords"] = torch.zeros(Bt, N, 2, device=self.dev, dtype=f32)
+            P.inp["masks"] = torch.zeros(Bt, N, device=self.dev, dtype=f32)
+        else:
+            P.inp["coords"] = torch.zeros(Bt, N, 4, device=self.dev, dtype=f32)
+            P.inp["masks"] = torch.zeros(Bt, N, device=self.dev, dtype=f32)
+            for si in range(S):
+                P.inp[f"feat{si}"] = torch.zeros(Bt, N, cfg.tok_in_dim, device=self.dev, dtype=f32)
+                P.inp[f"fmask{si}"] = torch.zeros(Bt, N, device=self.dev, dtype=f32)
+        P.out = torch.zeros(Bt, cfg.out_channels, Himg, Himg, device=self.dev, dtype=f32)
+
+        # ---- grounding tokens (PositionNet) -> objs [S, Bt*N, D] -----------------------------
+        D = cfg.tok_out_dim
+        pos_rows = self._buf(Bt * N * self.pos_k).view(Bt * N, self.pos_k)
+        hid1 = self._buf(Bt * N * cfg.tok_hidden).view(Bt * N, cfg.tok_hidden)
+        hid2 = self._buf(Bt * N * cfg.tok_hidden).view(Bt * N, cfg.tok_hidden)
+        objs = self._buf(S * Bt * N * D).view(S, Bt * N, D)
+        for si in range(S):
+            if cfg.tokenizer == "keypoint":
+                feat, fmask = W["pn.table"], P.inp["masks"]
+            else:
+                feat, fmask = P.inp[f"feat{si}"], P.inp[f"fmask{si}"]
+            nf = W[f"pn.s{si}.null_feat"]
+            P.add(f"pn{si}.features", lambda feat=feat, fmask=fmask, nf=nf: ops.position_features(
+                feat, fmask, nf, P.inp["coords"], P.inp["masks"], W["pn.null_pos"], pos_rows, cfg.fourier_freqs))
+            k = f"pn.s{si}"
+            P.add(f"pn{si}.l0", lambda k=k: ops.gemm(pos_rows, W[f"{k}.0.w"], hid1, bias=W[f"{k}.0.b"], act=ACT_SILU))
+            P.add(f"pn{si}.l2", lambda k=k: ops.gemm(hid1, W[f"{k}.2.w"], hid2, bias=W[f"{k}.2.b"], act=ACT_SILU))
+            P.add(f"pn{si}.l4", lambda k=k, si=si: ops.gemm(hid2, W[f"{k}.4.w"], objs[si], bias=W[f"{k}.4.b"]))
+
+        # ---- time embedding -------------------------------------------------------------------
+        ted = cfg.time_embed_dim
+        temb = self._buf(Bt * cfg.model_channels).view(Bt, cfg.model_channels)
+        e1 = self._buf(Bt * ted).view(Bt, ted)
+        e2 = self._buf(Bt * ted).view(Bt, ted)
+        emb_all = torch.zeros(Bt, self.emb_total, device=self.dev, dtype=f32)
+        P.add("temb", lambda: ops.timestep_embedding(P.inp["t"], temb))
+        P.add("time_embed.0", lambda: ops.gemm(temb, W["time_embed.0.w"], e1, bias=W["time_embed.0.b"], act=ACT_SILU))
+        # only SiLU(emb) is ever consumed (openaimodel.py:171-177): fold the SiLU into this epilogue
+        P.add("time_embed.2", lambda: ops.gemm(e1, W["time_embed.2.w"], e2, bias=W["time_embed.2.b"], act=ACT_SILU))
+        P.add("emb_layers", lambda: ops.gemm(e2, W["emb_all.w"], emb_all, bias=W["emb_all.b"]))
+
+        # ---- context -> bf16 -------------------------------------------------------------------
+        ctx_a = self._buf(Bt * nctx * cfg.context_dim).view(Bt * nctx, cfg.context_dim)
+        P.add("context.cast", lambda: ops.cast(P.inp["context"], ctx_a))
+
+        # ---- concat buffers: one per output block; producers write their channel slice --------
+        out_blocks = [b for b in self.blocks if b.where == "out"]
+        in_blocks = [b for b in self.blocks if b.where == "in"]
+        mid = [b for b in self.blocks if b.where == "mid"][0]
+        cats = []
+        for ob in out_blocks:
+            hw = (Himg // ob.ds) ** 2
+            ctot = ob.layers[0].cin
+            cats.append(self._buf(Bt * hw * ctot).view(Bt, hw, ctot))
+        dest: Dict[Tuple[str, int], torch.Tensor] = {}
+        for j, ib in enumerate(in_blocks):                # skip stack pops in reverse order
+            ob_i = len(in_blocks) - 1 - j
+            ch_h = out_blocks[ob_i].layers[0].cin - out_blocks[ob_i].skip_ch
+            assert out_blocks[ob_i].skip_ch == ib.out_ch
+            dest[("in", ib.index)] = cats[ob_i][:, :, ch_h:]
+        dest[("mid", 0)] = cats[0][:, :, : mid.out_ch]
+        for i, ob in enumerate(out_blocks):
+            if i + 1 < len(out_blocks):
+                dest[("out", ob.index)] = cats[i + 1][:, :, : ob.out_ch]
+            else:
+                dest[("out", ob.index)] = self._buf(Bt * Himg * Himg * ob.out_ch).view(Bt, Himg * Himg, ob.out_ch)
+
+        st_index = {p: i for i, p in enumerate(self.st_prefixes)}
+
+        # ---- layer emitters --------------------------------------------------------------------
+        def emit_res(ly, x, out, H):
+            p, hw = ly.prefix, H * H
+            a = view("t0", Bt, hw, ly.cin)
+            h1 = view("sb", Bt, hw, ly.cout)
+            a2 = view("sc", Bt, hw, ly.cout)
+            off = self.emb_off[p]
+            rb = emb_all[:, off: off + ly.cout]
+            P.add(f"{p}.gn1", lambda: ops.groupnorm(x, a, W[f"{p}.gn1.g"], W[f"{p}.gn1.b"], stats, 32, 1e-5, True))
+            P.add(f"{p}.conv1", lambda: ops.gemm(a, W[f"{p}.conv1.w"], h1, bias=W[f"{p}.conv1.b"], rowbias=rb,
+                                                 rows_per_batch=hw, conv=(Bt, H, H)))
+            P.add(f"{p}.gn2", lambda: ops.groupnorm(h1, a2, W[f"{p}.gn2.g"], W[f"{p}.gn2.b"], stats, 32, 1e-5, True))
+            if ly.cin != ly.cout:
+                sk = view("sd", Bt, hw, ly.cout)
+                P.add(f"{p}.skip", lambda: ops.gemm(x, W[f"{p}.skip.w"], sk, bias=W[f"{p}.skip.b"]))
+                res = sk
+            else:
+                res = x
+            P.add(f"{p}.conv2", lambda: ops.gemm(a2, W[f"{p}.conv2.w"], out, bias=W[f"{p}.conv2.b"], residual=res, conv=(Bt, H, H)))
+
+        def emit_st(ly, x_in, out, H):
+            p, T, C = ly.prefix, H * H, ly.cin
+            tb = f"{p}.transformer_blocks.0"
+            heads, d = ly.heads, ly.d_head
+            gi = st_index[p]
+            t0 = view("t0", Bt, T, C)
+            xs = view("xs", Bt, T, C)
+            ao = view("ao", Bt, T, C)
+            ffh = view("ffh", Bt, T, 4 * C)
+            qkv = view("qkv", Bt, T, 3 * C)
+            P.add(f"{p}.gn", lambda: ops.groupnorm(x_in, t0, W[f"{p}.gn.g"], W[f"{p}.gn.b"], stats, 32, 1e-6, False))
+            P.add(f"{p}.proj_in", lambda: ops.gemm(t0, W[f"{p}.proj_in.w"], xs, bias=W[f"{p}.proj_in.b"]))
+            # -- attn1 (attention.py:334)
+            P.add(f"{tb}.norm1", lambda: ops.layernorm(xs, t0, W[f"{tb}.norm1.g"], W[f"{tb}.norm1.b"]))
+            P.add(f"{tb}.attn1.qkv", lambda: ops.gemm(t0, W[f"{tb}.attn1.qkv.w"], qkv))
+            P.add(f"{tb}.attn1.core", lambda: ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], ao, heads, d))
+            P.add(f"{tb}.attn1.out", lambda: ops.gemm(ao, W[f"{tb}.attn1.out.w"], xs, bias=W[f"{tb}.attn1.out.b"], residual=xs))
+            # -- fuser: GatedSelfAttentionDense (attention.py:236-244); skipped when scale == 0
+            fu = f"{tb}.fuser"
+            objp = view("objp", S, Bt, N, C)
+            ln = view("ln", Bt, T + G, C)
+            qkv2 = view("qkv", Bt, T + G, 3 * C)
+            P.add(f"{fu}.linear", lambda: ops.gemm(objs.view(S * Bt * N, D), W[f"{fu}.linear.w"], objp.view(S * Bt * N, C),
+                                                  bias=W[f"{fu}.linear.b"]), fuser=True)
+            P.add(f"{fu}.norm1.x", lambda: ops.layernorm(xs, ln[:, :T], W[f"{fu}.norm1.g"], W[f"{fu}.norm1.b"]), fuser=True)
+            for si in range(S):
+                P.add(f"{fu}.norm1.objs{si}", lambda si=si: ops.layernorm(objp[si], ln[:, T + si * N: T + (si + 1) * N],
+                                                                         W[f"{fu}.norm1.g"], W[f"{fu}.norm1.b"]), fuser=True)
+            P.add(f"{fu}.attn.qkv", lambda: ops.gemm(ln, W[f"{fu}.attn.qkv.w"], qkv2), fuser=True)
+            P.add(f"{fu}.attn.core", lambda: ops.attention(qkv2[:, :T, :C], qkv2[:, :, C:2 * C], qkv2[:, :, 2 * C:], ao, heads, d), fuser=True)
+            P.add(f"{fu}.attn.out", lambda: ops.gemm(ao, W[f"{fu}.attn.out.w"], xs, bias=W[f"{fu}.attn.out.b"],
+                                                    gate=W["gates"][gi, 0:1], residual=xs), fuser=True)
+            P.add(f"{fu}.norm2", lambda: ops.layernorm(xs, t0, W[f"{fu}.norm2.g"], W[f"{fu}.norm2.b"]), fuser=True)
+            P.add(f"{fu}.ff.1", lambda: ops.gemm(t0, W[f"{fu}.ff.w1"], ffh, bias=W[f"{fu}.ff.b1"], geglu=True), fuser=True)
+            P.add(f"{fu}.ff.2", lambda: ops.gemm(ffh, W[f"{fu}.ff.w2"], xs, bias=W[f"{fu}.ff.b2"], gate=W["gates"][gi, 1:2], residual=xs), fuser=True)
+            # -- attn2: cross attention to the text context (attention.py:336)
+            q = view("ao", Bt, T, C)            # ao is free between attention calls: reuse as Q, write O to t0
+            kv = view("kv", Bt, nctx, 2 * C)
+            P.add(f"{tb}.norm2", lambda: ops.layernorm(xs, t0, W[f"{tb}.norm2.g"], W[f"{tb}.norm2.b"]))
+            P.add(f"{tb}.attn2.q", lambda: ops.gemm(t0, W[f"{tb}.attn2.q.w"], q))
+            P.add(f"{tb}.attn2.kv", lambda: ops.gemm(ctx_a, W[f"{tb}.attn2.kv.w"], kv))
+            P.add(f"{tb}.attn2.core", lambda: ops.attention(q, kv[:, :, :C], kv[:, :, C:], t0, heads, d))
+            P.add(f"{tb}.attn2.out", lambda: ops.gemm(t0, W[f"{tb}.attn2.out.w"], xs, bias=W[f"{tb}.attn2.out.b"], residual=xs))
+            # -- ff (attention.py:337)
+            P.add(f"{tb}.norm3", lambda: ops.layernorm(xs, t0, W[f"{tb}.norm3.g"], W[f"{tb}.norm3.b"]))
+            P.add(f"{tb}.ff.1", lambda: ops.gemm(t0, W[f"{tb}.ff.w1"], ffh, bias=W[f"{tb}.ff.b1"], geglu=True))
+            P.add(f"{tb}.ff.2", lambda: ops.gemm(ffh, W[f"{tb}.ff.w2"], xs, bias=W[f"{tb}.ff.b2"], residual=xs))
+            P.add(f"{p}.proj_out", lambda: ops.gemm(xs, W[f"{p}.proj_out.w"], out, bias=W[f"{p}.proj_out.b"], residual=x_in))
+
+        def emit_down(ly, x, out, H):
+            p = ly.prefix
+            Ho = H // 2
+            col = view("col", Bt * Ho * Ho, 9 * ly.cin)
+            P.add(f"{p}.im2col", lambda: ops.im2col_s2(x, col, H, H))
+            P.add(f"{p}.conv", lambda: ops.gemm(col, W[f"{p}.w"], out, bias=W[f"{p}.b"]))
+
+        def emit_up(ly, x, out, H):
+            p = ly.prefix
+            up = view("up", Bt, 4 * H * H, ly.cin)
+            P.add(f"{p}.upsample", lambda: ops.upsample2x(x, up, H, H))
+            P.add(f"{p}.conv", lambda: ops.gemm(up, W[f"{p}.w"], out, bias=W[f"{p}.b"], conv=(Bt, 2 * H, 2 * H)))
+
+        # ---- walk the blocks ---------------------------------------------------------------------
+        h = None
+        oi = 0
+        for blk in self.blocks:
+            H = Himg // blk.ds
+            if blk.where == "out":
+                h = cats[oi]
+                oi += 1
+            final = dest[(blk.where, blk.index)]
+            tmp_names = ["blk", "blk2"]
+            for li, ly in enumerate(blk.layers):
+                last = li == len(blk.layers) - 1
+                o = final if last else view(tmp_names[li % 2], Bt, H * H, ly.cout)
+                if ly.kind == "conv_in":
+                    extra = P.inp.get("extra")
+                    P.add("conv_in", lambda o=o, extra=extra: ops.conv_in(P.inp["x"], extra, W["conv_in.w"], W["conv_in.b"], o))
+                elif ly.kind == "res":
+                    emit_res(ly, h, o, H)
+                elif ly.kind == "st":
+                    emit_st(ly, h, o, H)
+                elif ly.kind == "down":
+                    emit_down(ly, h, o, H)
+                elif ly.kind == "up":
+                    emit_up(ly, h, o, H)
+                h = o
+        # ---- out: GN + SiLU + conv3x3 -> eps (NCHW fp32) ----------------------------------------
+        mc = cfg.model_channels
+        fin = view("t0", Bt, Himg * Himg, mc)
+        hl = h
+        P.add("out.gn", lambda: ops.groupnorm(hl, fin, W["out.gn.g"], W["out.gn.b"], stats, 32, 1e-5, True))
+        P.add("out.conv", lambda: ops.conv_out(fin, W["out.w"], W["out.b"], P.out, Himg, Himg))
+        return P
+
+    # ------------------------------------------------------------------------------------------
+    # execution
+    # ------------------------------------------------------------------------------------------
+    def _plan(self, Bt: int, N: int, nctx: int) -> Plan:
+        key = (Bt, N, nctx)
+        if key not in self.plans:
+            self.plans[key] = self._build_plan(Bt, N, nctx)
+        return self.plans[key]
+
+    def _n_objs(self, grounding: Dict[str, torch.Tensor]) -> int:
+        return (grounding["points"] if self.cfg.tokenizer == "keypoint" else grounding["boxes"]).shape[1]
+
+    def _stage_grounding(self, P: Plan, grounding: Optional[Dict[str, torch.Tensor]], lo: int, hi: int) -> None:
+        """Copy grounding kwargs (GroundingNetInput.prepare output) into rows [lo, hi) of the static inputs;
+        None -> the null input (all zeros, grounding_input/*:get_null_input)."""
+        cfg = self.cfg
+        names = [k for k in P.inp if k in ("coords", "masks") or k.startswith(("feat", "fmask"))]
+        if grounding is None:
+            for k in names:
+                P.inp[k][lo:hi].zero_()
+            return
+        if cfg.tokenizer == "keypoint":
+            P.inp["coords"][lo:hi].copy_(grounding["points"])
+            P.inp["masks"][lo:hi].copy_(grounding["masks"])
+        elif cfg.tokenizer == "text":
+            P.inp["coords"][lo:hi].copy_(grounding["boxes"])
+            P.inp["masks"][lo:hi].copy_(grounding["masks"])
+            P.inp["feat0"][lo:hi].copy_(grounding["positive_embeddings"])
+            P.inp["fmask0"][lo:hi].copy_(grounding["masks"])
+        else:
+            P.inp["coords"][lo:hi].copy_(grounding["boxes"])
+            P.inp["masks"][lo:hi].copy_(grounding["masks"])
+            P.inp["feat0"][lo:hi].copy_(grounding["text_embeddings"])
+            P.inp["fmask0"][lo:hi].copy_(grounding["text_masks"])
+            P.inp["feat1"][lo:hi].copy_(grounding["image_embeddings"])
+            P.inp["fmask1"][lo:hi].copy_(grounding["image_masks"])
+
+    def _execute(self, P: Plan) -> None:
+        fuser_on = self.scale != 0.0
+        if not self.use_graphs:
+            P.run(fuser_on)
+            return
+        g = P.graphs.get(fuser_on)
+        if g is None:
+            # first call runs eagerly (creates the tensor maps, sets kernel attributes), second captures
+            n = P.warm.get(fuser_on, 0)
+            if n < 1:
+                P.run(fuser_on)
+                P.warm[fuser_on] = n + 1
+                return
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                P.run(fuser_on)
+            P.graphs[fuser_on] = g
+        g.replay()
+
+    @torch.no_grad()
+    def forward(self, x, timesteps, context, grounding, inpainting_extra_input=None) -> torch.Tensor:
+        """One UNet pass (UNetModel.forward semantics).  grounding=None -> null grounding tokens.
+        Returns a NEW fp32 tensor [B, out_channels, H, W]."""
+        assert self.loaded, "load_state_dict first"
+        B = x.shape[0]
+        N = self._n_objs(grounding) if grounding is not None else self._last_N
+        self._last_N = N
+        P = self._plan(B, N, context.shape[1])
+        P.inp["x"].copy_(x)
+        P.inp["t"].copy_(timesteps)
+        P.inp["context"].copy_(context)
+        if self.cfg.inpaint_mode:
+            P.inp["extra"].copy_(inpainting_extra_input)
+        self._stage_grounding(P, grounding, 0, B)
+        self._execute(P)
+        return P.out.clone()
+
+    @torch.no_grad()
+    def forward_cfg(self, x, timesteps, context, uc, grounding, inpainting_extra_input=None):
+        """cond + uncond (null grounding, context = uc) as ONE 2B-row pass.  Returns (eps_cond, eps_uncond)
+        as views of the static output (valid until the next call)."""
+        assert self.loaded
+        B = x.shape[0]
+        N = self._n_objs(grounding)
+        self._last_N = N
+        P = self._plan(2 * B, N, context.shape[1])
+        P.inp["x"][:B].copy_(x); P.inp["x"][B:].copy_(x)
+        P.inp["t"][:B].copy_(timesteps); P.inp["t"][B:].copy_(timesteps)
+        P.inp["context"][:B].copy_(context); P.inp["context"][B:].copy_(uc)
+        if self.cfg.inpaint_mode:
+            P.inp["extra"][:B].copy_(inpainting_extra_input); P.inp["extra"][B:].copy_(inpainting_extra_input)
+        self._stage_grounding(P, grounding, 0, B)
+        self._stage_grounding(P, None, B, 2 * B)
+        self._execute(P)
+        return P.out[:B], P.out[B:]

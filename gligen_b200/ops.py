@@ -1,0 +1,186 @@
+"""Operator layer of the engine: every method enqueues exactly the CUDA kernels of libgligen_b200.so on
+the current torch stream.  torch is used for memory and streams only.
+
+`CudaOps` is the product backend.  The engine is written against this interface so that tests can
+inject a torch-fp32 checker backend (tests/ref_ops.py) to validate the engine's wiring on a CPU-only box;
+the product never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import lib as L
+
+
+def _rows_view(t: torch.Tensor):
+    """(ptr, rows, cols, ld) of a tensor whose last dim is contiguous and whose leading dims collapse to
+    uniformly strided rows (e.g. a channel slice of a [B, HW, Ctot] concat buffer)."""
+    assert t.stride(-1) == 1, "last dim must be contiguous"
+    cols = t.shape[-1]
+    if t.dim() == 1:
+        return t.data_ptr(), 1, cols, cols
+    ld = t.stride(-2)
+    rows = t.shape[-2]
+    for i in range(t.dim() - 3, -1, -1):
+        assert t.shape[i] == 1 or t.stride(i) == t.stride(i + 1) * t.shape[i + 1], f"non-uniform row stride {t.shape} {t.stride()}"
+        rows *= t.shape[i]
+    return t.data_ptr(), rows, cols, ld
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class CudaOps:
+    """bf16 activations / fp32 statistics on one CUDA device."""
+
+    name = "cuda"
+    act_dtype = torch.bfloat16
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.GligenLibraryError("CudaOps needs a CUDA device (there is no CPU fallback)")
+        self.lib = L.load()
+
+    # -- helpers --------------------------------------------------------------------------------
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def launch_count(self) -> int:
+        return int(self.lib.glg_launch_count())
+
+    def reset_launch_count(self) -> None:
+        self.lib.glg_reset_launch_count()
+
+    # -- tensor-core GEMM / conv --------------------------------------------------------------
+    def gemm(self, a, w, out, bias=None, rowbias=None, rows_per_batch=1, act=0, gate=None, residual=None,
+             geglu=False, conv=None):
+        """out = epilogue(a @ w.T).  `conv=(B,H,W)` selects the implicit 3x3 convolution (w is [9*N, K])."""
+        ap, M, K, lda = _rows_view(a)
+        op, Mo, No, ldc = _rows_view(out)
+        g = L.GlgGemmArgs()
+        N = No * 2 if geglu else No
+        assert Mo == M, (Mo, M)
+        assert w.is_contiguous() and w.shape[1] == K and w.shape[0] == (9 * N if conv else N), (w.shape, N, K)
+        g.A, g.lda, g.W, g.out, g.ldc = ap, lda, w.data_ptr(), op, ldc
+        g.M, g.N, g.K = M, N, K
+        g.out_fp32 = 1 if out.dtype == torch.float32 else 0
+        g.bias = _ptr(bias)
+        if rowbias is not None:
+            rp, _, rc, rld = _rows_view(rowbias)
+            assert rc == N and rowbias.dtype == torch.float32
+            g.rowbias, g.ld_rowbias, g.rows_per_batch = rp, rld, rows_per_batch
+        else:
+            g.rowbias, g.ld_rowbias, g.rows_per_batch = None, 0, 1
+        g.act = act
+        g.gate = _ptr(gate)
+        if residual is not None:
+            rp, Mr, Nr, ldr = _rows_view(residual)
+            assert Mr == M and Nr == No
+            g.residual, g.ldr = rp, ldr
+        else:
+            g.residual, g.ldr = None, 0
+        g.geglu = 1 if geglu else 0
+        if conv is not None:
+            g.conv_mode, g.Bn, g.H, g.Wd = 1, conv[0], conv[1], conv[2]
+        else:
+            g.conv_mode, g.Bn, g.H, g.Wd = 0, 0, 0, 0
+        L.check(self.lib.glg_gemm(C.byref(g), self._stream()), "glg_gemm")
+
+    # -- attention ---------------------------------------------------------------------------------
+    def attention(self, q, k, v, out, heads: int, d_head: int):
+        """q [B, Lq, heads*d] / k, v [B, Lk, heads*d] strided views; out [B, Lq, heads*d]."""
+        a = L.GlgAttnArgs()
+        B, Lq, _ = q.shape
+        Lk = k.shape[1]
+        for t in (q, k, v, out):
+            assert t.stride(-1) == 1
+        a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+        a.q_row, a.k_row, a.v_row, a.o_row = q.stride(1), k.stride(1), v.stride(1), out.stride(1)
+        a.q_batch, a.k_batch, a.v_batch, a.o_batch = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
+        a.B, a.heads, a.d_head, a.Lq, a.Lk = B, heads, d_head, Lq, Lk
+        a.scale = float(d_head) ** -0.5
+        L.check(self.lib.glg_attention(C.byref(a), self._stream()), "glg_attention")
+
+    # -- norms ---------------------------------------------------------------------------------------
+    def groupnorm(self, x, y, gamma, beta, stats, groups: int, eps: float, silu: bool):
+        """x, y: [B, HW, C] (strided rows); stats: fp32 scratch [B*groups*2]."""
+        B, HW, Cc = x.shape
+        xp, _, _, ldx = _rows_view(x)
+        yp, _, _, ldy = _rows_view(y)
+        L.check(self.lib.glg_groupnorm(xp, ldx, yp, ldy, gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(),
+                                       B, HW, Cc, groups, eps, 1 if silu else 0, self._stream()), "glg_groupnorm")
+
+    def layernorm(self, x, y, gamma, beta, eps: float = 1e-5):
+        """x [B, rows, C] with contiguous rows inside a batch; y likewise (batch strides may differ)."""
+        B, rows, Cc = x.shape
+        assert x.stride(2) == 1 and x.stride(1) == Cc and y.stride(2) == 1 and y.stride(1) == Cc
+        L.check(self.lib.glg_layernorm(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), gamma.data_ptr(), beta.data_ptr(),
+                                       B, rows, Cc, eps, self._stream()), "glg_layernorm")
+
+    # -- small ops -----------------------------------------------------------------------------------
+    def conv_in(self, x, extra, w, bias, out):
+        B, C0, H, W = x.shape
+        assert x.is_contiguous() and x.dtype == torch.float32
+        C1 = 0 if extra is None else extra.shape[1]
+        if extra is not None:
+            assert extra.is_contiguous() and extra.dtype == torch.float32
+        op, _, Cout, ldo = _rows_view(out)
+        L.check(self.lib.glg_conv_in(x.data_ptr(), C0, _ptr(extra), C1, w.data_ptr(), bias.data_ptr(), op, ldo,
+                                     B, H, W, Cout, self._stream()), "glg_conv_in")
+
+    def conv_out(self, x, w, bias, out, H: int, W: int):
+        """x [B, HW, Cin] bf16 -> out [B, Cout, H, W] fp32."""
+        B, _, Cin = x.shape
+        xp, _, _, ldx = _rows_view(x)
+        assert out.is_contiguous() and out.dtype == torch.float32
+        L.check(self.lib.glg_conv_out(xp, ldx, w.data_ptr(), bias.data_ptr(), out.data_ptr(), B, H, W, Cin, out.shape[1],
+                                      self._stream()), "glg_conv_out")
+
+    def upsample2x(self, x, y, H: int, W: int):
+        B, _, Cc = x.shape
+        xp, _, _, ldx = _rows_view(x)
+        yp, _, _, ldy = _rows_view(y)
+        L.check(self.lib.glg_upsample2x(xp, ldx, yp, ldy, B, H, W, Cc, self._stream()), "glg_upsample2x")
+
+    def im2col_s2(self, x, y, H: int, W: int):
+        B, _, Cc = x.shape
+        xp, _, _, ldx = _rows_view(x)
+        assert y.is_contiguous()
+        L.check(self.lib.glg_im2col_s2(xp, ldx, y.data_ptr(), B, H, W, Cc, self._stream()), "glg_im2col_s2")
+
+    def timestep_embedding(self, t, out):
+        assert t.dtype == torch.int64 and out.is_contiguous()
+        L.check(self.lib.glg_timestep_embedding(t.data_ptr(), out.data_ptr(), out.shape[0], out.shape[1], self._stream()),
+                "glg_timestep_embedding")
+
+    def position_features(self, feat, feat_mask, null_feat, coords, pos_mask, null_pos, out, freqs: int):
+        """feat [B,N,F] or [N,F] (broadcast) fp32; coords [B,N,nc]; out [B*N, ldo] bf16."""
+        B, N, nc = coords.shape
+        F_ = feat.shape[-1]
+        fbs = 0 if feat.dim() == 2 else feat.stride(0)
+        for t in (feat, feat_mask, null_feat, coords, pos_mask, null_pos):
+            assert t.is_contiguous() and t.dtype == torch.float32
+        assert out.is_contiguous()
+        L.check(self.lib.glg_position_features(feat.data_ptr(), fbs, feat_mask.data_ptr(), null_feat.data_ptr(), coords.data_ptr(),
+                                               pos_mask.data_ptr(), null_pos.data_ptr(), out.data_ptr(), out.shape[-1],
+                                               B, N, F_, nc, freqs, self._stream()), "glg_position_features")
+
+    def cast(self, x, y):
+        """fp32 -> activation dtype, contiguous."""
+        assert x.is_contiguous() and y.is_contiguous() and x.dtype == torch.float32 and x.numel() == y.numel()
+        L.check(self.lib.glg_cast_f32_bf16(x.data_ptr(), y.data_ptr(), x.numel(), self._stream()), "glg_cast_f32_bf16")
+
+    def sampler_update(self, x, e_cond, e_uncond, guidance, olds, coefs, a_t, a_prev, e_out, x_prev):
+        o = list(olds) + [None] * (3 - len(olds))
+        for t in (x, e_cond, x_prev):
+            assert t.is_contiguous() and t.dtype == torch.float32
+        L.check(self.lib.glg_sampler_update(x.data_ptr(), e_cond.data_ptr(), _ptr(e_uncond), float(guidance),
+                                            _ptr(o[0]), _ptr(o[1]), _ptr(o[2]),
+                                            float(coefs[0]), float(coefs[1]), float(coefs[2]), float(coefs[3]),
+                                            float(a_t), float(a_prev), _ptr(e_out), x_prev.data_ptr(), x.numel(), self._stream()),
+                "glg_sampler_update")

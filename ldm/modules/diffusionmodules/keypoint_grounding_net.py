@@ -1,0 +1,7 @@
+"""Grounding tokeniser container (keypoint); the MLP + Fourier features run in gligen_b200.engine
+(kernels glg_position_features + glg_gemm).  Reference: ldm/modules/diffusionmodules/keypoint_grounding_net.py."""
+from ldm.modules.diffusionmodules.grounding_common import make_position_net
+
+
+class PositionNet(make_position_net("keypoint")):
+    pass

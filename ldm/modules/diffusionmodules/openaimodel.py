@@ -1,0 +1,197 @@
+"""Drop-in `UNetModel` at the reference's import path (ldm.modules.diffusionmodules.openaimodel.UNetModel,
+located by string through instantiate_from_config; reference openaimodel.py:237-464).
+
+Same constructor kwargs, same state_dict keys/shapes, same `forward(input: dict) -> eps` contract, same
+externally visible attributes (`image_size`, `in_channels`, `inpaint_mode`, `grounding_tokenizer_input`,
+`first_conv_type`, `restore_first_conv_from_SD`, fuser modules with `.scale`).  The arithmetic is NOT
+PyTorch: forward() hands raw device pointers to libgligen_b200.so (hand-written sm_100a kernels) through
+gligen_b200.engine.  There is no CPU / eager fallback: parameters must live on a CUDA device.
+"""
+import os
+import re
+from copy import deepcopy
+
+import torch
+import torch.nn as nn
+
+from gligen_b200.spec import UNetConfig, unet_param_shapes
+from ldm.modules.attention import (BasicTransformerBlock, CrossAttention, FeedForward, GatedSelfAttentionDense,
+                                   ParamNode, SelfAttention, SpatialTransformer)
+from ldm.modules.diffusionmodules.grounding_common import attach_params, tokenizer_config
+from ldm.util import instantiate_from_config
+
+_TOKENIZERS = {
+    "ldm.modules.diffusionmodules.text_grounding_net.PositionNet": "text",
+    "ldm.modules.diffusionmodules.text_image_grounding_net.PositionNet": "text_image",
+    "ldm.modules.diffusionmodules.keypoint_grounding_net.PositionNet": "keypoint",
+}
+
+
+class TimestepEmbedSequential(ParamNode):
+    pass
+
+
+class ResBlock(ParamNode):
+    pass
+
+
+class Downsample(ParamNode):
+    pass
+
+
+class Upsample(ParamNode):
+    pass
+
+
+def _node_class(path: str):
+    """Container type for a module path (purely cosmetic except for the fuser, which set_alpha_scale finds by type)."""
+    if re.fullmatch(r"(input_blocks|output_blocks)\.\d+|middle_block", path):
+        return TimestepEmbedSequential
+    if path.endswith(".fuser"):
+        return GatedSelfAttentionDense
+    if path.endswith((".attn1", ".fuser.attn")):
+        return SelfAttention
+    if path.endswith(".attn2"):
+        return CrossAttention
+    if path.endswith(".ff"):
+        return FeedForward
+    if re.search(r"transformer_blocks\.\d+$", path):
+        return BasicTransformerBlock
+    return ParamNode
+
+
+class UNetModel(ParamNode):
+    def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
+                 dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, use_checkpoint=False, num_heads=8,
+                 use_scale_shift_norm=False, transformer_depth=1, context_dim=None, fuser_type=None, inpaint_mode=False,
+                 grounding_downsampler=None, grounding_tokenizer=None):
+        super().__init__()
+        assert fuser_type in ["gatedSA", "gatedSA2", "gatedCA"]
+        unsupported = []
+        if fuser_type != "gatedSA":
+            unsupported.append(f"fuser_type={fuser_type} (every shipped config uses gatedSA)")
+        if grounding_downsampler is not None:
+            unsupported.append("grounding_downsampler (spatial-map modalities are outside the accelerated path)")
+        if use_scale_shift_norm or transformer_depth != 1 or dims != 2 or not conv_resample or dropout:
+            unsupported.append("use_scale_shift_norm / transformer_depth != 1 / dims != 2 / conv_resample=False / dropout")
+        target = (grounding_tokenizer or {}).get("target")
+        if target not in _TOKENIZERS:
+            unsupported.append(f"grounding_tokenizer target {target!r}")
+        if unsupported:
+            raise NotImplementedError("gligen_b200 UNetModel: " + "; ".join(unsupported))
+
+        self.image_size = image_size
+        self.in_channels = in_channels
+        self.model_channels = model_channels
+        self.out_channels = out_channels
+        self.num_res_blocks = num_res_blocks
+        self.attention_resolutions = attention_resolutions
+        self.dropout = dropout
+        self.channel_mult = channel_mult
+        self.conv_resample = conv_resample
+        self.use_checkpoint = use_checkpoint
+        self.num_heads = num_heads
+        self.context_dim = context_dim
+        self.fuser_type = fuser_type
+        self.inpaint_mode = inpaint_mode
+        self.grounding_tokenizer_input = None          # set externally (gligen_inference.py:349)
+        self.downsample_net = None
+        self.additional_channel_from_downsampler = 0
+        self.first_conv_type = "SD"
+        self.first_conv_restorable = not inpaint_mode
+
+        base = UNetConfig(image_size=image_size, in_channels=in_channels, out_channels=out_channels,
+                          model_channels=model_channels, num_res_blocks=num_res_blocks,
+                          attention_resolutions=tuple(attention_resolutions), channel_mult=tuple(channel_mult),
+                          num_heads=num_heads, transformer_depth=transformer_depth, context_dim=context_dim,
+                          fuser_type=fuser_type, inpaint_mode=inpaint_mode)
+        self.cfg = tokenizer_config(_TOKENIZERS[target], base, **grounding_tokenizer.get("params", {}))
+        shapes = unet_param_shapes(self.cfg)
+        body = {k: v for k, v in shapes.items() if not k.startswith("position_net.")}
+        attach_params(self, body, "", _node_class)
+        self.position_net = instantiate_from_config(grounding_tokenizer)
+        self._fusers = [m for m in self.modules() if type(m) == GatedSelfAttentionDense]
+        self._engine = None
+        self._engine_stale = True
+        self._sd_conv_cache = None
+
+    # ---- weights ---------------------------------------------------------------------------------
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._engine_stale = True
+        return out
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)              # .to(device) / .cuda(): re-pack on the next forward
+        self._engine_stale = True
+        self._engine = None
+        return out
+
+    def engine(self):
+        """The native engine bound to this module's parameters (built lazily on the parameters' device)."""
+        dev = self.time_embed[0].weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("gligen_b200 UNetModel runs only on a CUDA device (sm_100a kernels); "
+                               "there is no CPU fallback - call .to('cuda') first")
+        if self._engine is None:
+            from gligen_b200.engine import Engine
+            from gligen_b200.ops import CudaOps
+            self._engine = Engine(self.cfg, CudaOps(dev))
+            self._engine_stale = True
+        if self._engine_stale:
+            self._engine.load_state_dict(self.state_dict())
+            self._engine_stale = False
+        return self._engine
+
+    def restore_first_conv_from_SD(self):
+        """reference openaimodel.py:400-413: swap input_blocks[0][0] for SD's 4->C conv, read from the
+        CWD-relative file "SD_input_conv_weight_bias.pth"."""
+        if not self.first_conv_restorable:
+            print("First conv layer is not restorable and skipped this process, probably because this is an inpainting model?")
+            return
+        conv = self.input_blocks[0][0]
+        path = "SD_input_conv_weight_bias.pth"
+        stamp = (os.path.abspath(path), os.path.getmtime(path))
+        if self._sd_conv_cache is None or self._sd_conv_cache[0] != stamp:
+            sd = torch.load(path, map_location="cpu")
+            self._sd_conv_cache = (stamp, sd["weight"].float(), sd["bias"].float())
+            self._sd_applied = False
+        if getattr(self, "_sd_applied", False) and self.first_conv_type == "SD" and hasattr(self, "GLIGEN_first_conv_state_dict"):
+            return                                       # already swapped in: idempotent
+        _, w, b = self._sd_conv_cache
+        if tuple(w.shape) != tuple(conv.weight.shape):
+            raise RuntimeError(f"{path}: weight {tuple(w.shape)} does not fit the first conv {tuple(conv.weight.shape)}")
+        self.GLIGEN_first_conv_state_dict = deepcopy(conv.state_dict())
+        with torch.no_grad():
+            conv.weight.copy_(w)
+            conv.bias.copy_(b)
+        if self._engine is not None and not self._engine_stale:
+            self._engine.set_first_conv(conv.weight, conv.bias)
+        self.first_conv_type = "SD"
+        self._sd_applied = True
+
+    # ---- forward -----------------------------------------------------------------------------------
+    def _sync_scales(self, eng):
+        scales = [float(m.scale) for m in self._fusers]
+        if getattr(eng, "scales", None) != scales:
+            eng.set_scale(scales)
+
+    def _grounding(self, input):
+        if "grounding_input" in input:
+            return input["grounding_input"]
+        return self.grounding_tokenizer_input.get_null_input()       # guidance null case (openaimodel.py:422-426)
+
+    @torch.no_grad()
+    def forward(self, input):
+        eng = self.engine()
+        self._sync_scales(eng)
+        return eng.forward(input["x"], input["timesteps"], input["context"], self._grounding(input),
+                           input.get("inpainting_extra_input") if self.inpaint_mode else None)
+
+    @torch.no_grad()
+    def forward_cfg(self, input, uc):
+        """cond + uncond in one 2B-row pass (used by the samplers in this repo; same results as two calls)."""
+        eng = self.engine()
+        self._sync_scales(eng)
+        return eng.forward_cfg(input["x"], input["timesteps"], input["context"], uc, input["grounding_input"],
+                               input.get("inpainting_extra_input") if self.inpaint_mode else None)

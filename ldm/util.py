@@ -1,0 +1,35 @@
+"""Config -> object glue kept at the reference's import path (reference ldm/util.py:71-86): the checkpoint's
+config_dict names classes by dotted string, so `instantiate_from_config` is how the drop-in UNetModel,
+samplers' diffusion object and grounding adapters are located."""
+import importlib
+
+
+def exists(x):
+    return x is not None
+
+
+def default(val, d):
+    if val is not None:
+        return val
+    return d() if callable(d) else d
+
+
+def get_obj_from_str(string, reload=False):
+    module, cls = string.rsplit(".", 1)
+    mod = importlib.import_module(module)
+    if reload:
+        mod = importlib.reload(mod)
+    return getattr(mod, cls)
+
+
+def instantiate_from_config(config):
+    if "target" not in config:
+        raise KeyError("Expected key `target` to instantiate.")
+    return get_obj_from_str(config["target"])(**config.get("params", dict()))
+
+
+def count_params(model, verbose=False):
+    n = sum(p.numel() for p in model.parameters())
+    if verbose:
+        print(f"{model.__class__.__name__} has {n * 1.e-6:.2f} M params.")
+    return n

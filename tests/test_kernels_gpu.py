@@ -1,0 +1,249 @@
+"""Per-kernel parity on the GPU: every CudaOps method (C-ABI call into libgligen_b200.so) against the
+same-named torch-fp32 statement in tests/ref_ops.py, on identical bf16-rounded inputs.
+
+Tolerances (floating point): outputs are bf16, accumulation fp32 -> rel-L2 <= 6e-3, max-abs <= 3% of max|ref|
+(attention: P is rounded to bf16 before PV, rel-L2 <= 1e-2)."""
+import pytest
+import torch
+
+from conftest import assert_close
+from ref_ops import RefOps
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from gligen_b200.ops import CudaOps
+    return CudaOps("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return RefOps("cuda:0", torch.float32)
+
+
+def rnd(*shape, scale=1.0, seed=0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to("cuda:0").to(dtype)
+
+
+GEMM_CASES = [
+    # M, N, K, flags
+    (256, 320, 320, dict()),
+    (1000, 640, 768, dict(bias=True)),
+    (300, 1280, 1280, dict(bias=True, residual=True, gate=True)),
+    (4, 5120, 1280, dict(bias=True, fp32=True)),
+    (2 * 77, 640, 768, dict()),
+    (512, 1920, 640, dict(bias=True, act=True)),
+    (16384, 960, 320, dict()),
+    (4096, 320, 1280, dict(bias=True, residual=True, strided=True)),
+    (4096, 2560, 320, dict(geglu=True)),
+    (700, 1024, 256, dict(geglu=True)),
+    (512, 640, 320, dict(bias=True, rowbias=128)),
+]
+
+
+@pytest.mark.parametrize("M,N,K,fl", GEMM_CASES)
+@pytest.mark.parametrize("force_bn", [0, 64, 128, 160, 256])
+def test_gemm(ops, ref, M, N, K, fl, force_bn):
+    if force_bn and (N % force_bn or fl.get("geglu")):
+        pytest.skip("BN does not divide N")
+    if force_bn and M > 5000:
+        pytest.skip("large case only with the heuristic tile")
+    a = rnd(M, K)
+    w = rnd(N, K, scale=K ** -0.5, seed=1)
+    geglu = fl.get("geglu", False)
+    No = N // 2 if geglu else N
+    bias = rnd(N, seed=2, dtype=torch.float32) if (fl.get("bias") or geglu) else None
+    gate = torch.tensor([0.37], device="cuda:0") if fl.get("gate") else None
+    rows_per_batch = fl.get("rowbias", 0)
+    rowbias = rnd(M // rows_per_batch, N, seed=3, dtype=torch.float32) if rows_per_batch else None
+    odt = torch.float32 if fl.get("fp32") else torch.bfloat16
+    if fl.get("strided"):
+        big = torch.zeros(M, No + 64, device="cuda:0", dtype=odt)
+        out, out_r = big[:, 64:], torch.zeros(M, No, device="cuda:0", dtype=odt)
+        resb = rnd(M, No + 128, seed=4)
+        residual = resb[:, 128:]
+    else:
+        out, out_r = torch.zeros(M, No, device="cuda:0", dtype=odt), torch.zeros(M, No, device="cuda:0", dtype=odt)
+        residual = rnd(M, No, seed=4) if fl.get("residual") else None
+    kw = dict(bias=bias, rowbias=rowbias, rows_per_batch=max(rows_per_batch, 1), act=1 if fl.get("act") else 0,
+              gate=gate, residual=residual, geglu=geglu)
+    ops.lib.glg_debug_force_bn(force_bn)
+    try:
+        ops.gemm(a, w, out, **kw)
+        torch.cuda.synchronize()
+    finally:
+        ops.lib.glg_debug_force_bn(0)
+    ref.gemm(a, w, out_r, **kw)
+    assert_close(out, out_r, what=f"gemm {M}x{N}x{K} {fl} bn={force_bn}")
+    if fl.get("strided"):
+        assert big[:, :64].abs().max().item() == 0.0, "wrote outside the output slice"
+
+
+CONV_CASES = [
+    # B, H, W, Cin, Cout, flags
+    (2, 64, 64, 320, 320, dict(rowbias=True)),
+    (2, 32, 32, 640, 1280, dict(residual=True)),
+    (1, 16, 16, 2560, 1280, dict()),
+    (3, 8, 8, 1280, 1280, dict(rowbias=True, residual=True)),
+    (1, 8, 8, 1280, 1280, dict()),
+    (2, 16, 16, 64, 64, dict()),
+    (2, 2, 2, 256, 256, dict(residual=True)),
+    (2, 4, 4, 128, 256, dict()),
+    (2, 64, 64, 320, 320, dict(strided=True)),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,fl", CONV_CASES)
+def test_conv3x3(ops, ref, B, H, W, Cin, Cout, fl):
+    if fl.get("strided"):
+        big = rnd(B, H * W, Cin + 192)
+        a = big[:, :, 64:64 + Cin]
+    else:
+        a = rnd(B, H * W, Cin)
+    w = rnd(9 * Cout, Cin, scale=(9 * Cin) ** -0.5, seed=1)
+    bias = rnd(Cout, seed=2, dtype=torch.float32)
+    rowbias = rnd(B, Cout, seed=3, dtype=torch.float32) if fl.get("rowbias") else None
+    residual = rnd(B, H * W, Cout, seed=4) if fl.get("residual") else None
+    out = torch.zeros(B, H * W, Cout, device="cuda:0", dtype=torch.bfloat16)
+    out_r = torch.zeros_like(out)
+    kw = dict(bias=bias, rowbias=rowbias, rows_per_batch=H * W, residual=residual, conv=(B, H, W))
+    ops.gemm(a, w, out, **kw)
+    torch.cuda.synchronize()
+    ref.gemm(a, w, out_r, **kw)
+    assert_close(out, out_r, what=f"conv {B}x{H}x{W} {Cin}->{Cout} {fl}")
+
+
+ATTN_CASES = [
+    # B, heads, d, Lq, Lk, packed
+    (1, 8, 40, 4096, 4096, "qkv"),
+    (2, 8, 40, 1024, 1054, "fuser"),
+    (2, 8, 80, 1024, 1084, "fuser"),
+    (2, 8, 160, 256, 286, "fuser"),
+    (3, 8, 160, 64, 94, "fuser"),
+    (2, 8, 40, 4096, 77, "kv"),
+    (2, 8, 80, 1024, 77, "kv"),
+    (2, 8, 160, 64, 77, "kv"),
+    (2, 8, 8, 256, 262, "fuser"),
+    (2, 8, 16, 64, 70, "fuser"),
+    (2, 8, 32, 16, 22, "fuser"),
+    (2, 4, 64, 200, 333, "plain"),
+]
+
+
+@pytest.mark.parametrize("B,heads,d,Lq,Lk,mode", ATTN_CASES)
+def test_attention(ops, ref, B, heads, d, Lq, Lk, mode):
+    C = heads * d
+    if mode == "qkv":
+        qkv = rnd(B, Lk, 3 * C)
+        q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+    elif mode == "fuser":
+        qkv = rnd(B, Lk, 3 * C)
+        q, k, v = qkv[:, :Lq, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+    elif mode == "kv":
+        q = rnd(B, Lq, C)
+        kv = rnd(B, Lk, 2 * C, seed=1)
+        k, v = kv[:, :, :C], kv[:, :, C:]
+    else:
+        q, k, v = rnd(B, Lq, C), rnd(B, Lk, C, seed=1), rnd(B, Lk, C, seed=2)
+    out = torch.zeros(B, Lq, C, device="cuda:0", dtype=torch.bfloat16)
+    out_r = torch.zeros_like(out)
+    ops.attention(q, k, v, out, heads, d)
+    torch.cuda.synchronize()
+    ref.attention(q, k, v, out_r, heads, d)
+    assert_close(out, out_r, rel=1e-2, max_rel=5e-2, what=f"attention d={d} {Lq}x{Lk} {mode}")
+
+
+@pytest.mark.parametrize("B,HW,C,ld,eps,silu", [(2, 4096, 320, 320, 1e-5, True), (2, 1024, 960, 960, 1e-5, True),
+                                                (1, 256, 2560, 2560, 1e-5, True), (3, 64, 1280, 1280, 1e-6, False),
+                                                (2, 1024, 640, 1280, 1e-5, True), (2, 4, 256, 256, 1e-5, True),
+                                                (2, 256, 64, 128, 1e-6, False)])
+def test_groupnorm(ops, ref, B, HW, C, ld, eps, silu):
+    big = rnd(B, HW, ld) * 1.7 + 0.3
+    x = big[:, :, ld - C:]
+    gamma = 1 + 0.1 * rnd(C, seed=1, dtype=torch.float32)
+    beta = 0.1 * rnd(C, seed=2, dtype=torch.float32)
+    stats = torch.zeros(B * 32 * 2, device="cuda:0")
+    y, y_r = torch.zeros(B, HW, C, device="cuda:0", dtype=torch.bfloat16), torch.zeros(B, HW, C, device="cuda:0", dtype=torch.bfloat16)
+    ops.groupnorm(x, y, gamma, beta, stats, 32, eps, silu)
+    torch.cuda.synchronize()
+    ref.groupnorm(x, y_r, gamma, beta, stats, 32, eps, silu)
+    assert_close(y, y_r, what="groupnorm")
+
+
+@pytest.mark.parametrize("B,rows,C", [(2, 4096, 320), (2, 30, 640), (3, 64, 1280), (2, 16, 64), (2, 7, 2048)])
+def test_layernorm(ops, ref, B, rows, C):
+    x = rnd(B, rows, C) * 2 + 0.5
+    gamma = 1 + 0.1 * rnd(C, seed=1, dtype=torch.float32)
+    beta = 0.1 * rnd(C, seed=2, dtype=torch.float32)
+    big = torch.zeros(B, rows + 5, C, device="cuda:0", dtype=torch.bfloat16)
+    big_r = torch.zeros_like(big)
+    ops.layernorm(x, big[:, 5:], gamma, beta)
+    torch.cuda.synchronize()
+    ref.layernorm(x, big_r[:, 5:], gamma, beta)
+    assert_close(big, big_r, what="layernorm")
+
+
+def test_small_ops(ops, ref):
+    dev = "cuda:0"
+    # conv_in (4 and 9 input channels)
+    for C1 in (0, 5):
+        x = rnd(2, 4, 64, 64, dtype=torch.float32)
+        extra = rnd(2, C1, 64, 64, seed=1, dtype=torch.float32) if C1 else None
+        w = rnd(9, 4 + C1, 320, scale=0.2, seed=2, dtype=torch.float32)
+        b = rnd(320, seed=3, dtype=torch.float32)
+        big = torch.zeros(2, 4096, 640, device=dev, dtype=torch.bfloat16)
+        out_r = torch.zeros(2, 4096, 320, device=dev, dtype=torch.bfloat16)
+        ops.conv_in(x, extra, w, b, big[:, :, 320:])
+        ref.conv_in(x, extra, w, b, out_r)
+        assert_close(big[:, :, 320:], out_r, what="conv_in")
+        assert big[:, :, :320].abs().max().item() == 0
+    # conv_out
+    x = rnd(2, 4096, 320)
+    w = rnd(9, 4, 320, scale=0.02, seed=1, dtype=torch.float32)
+    b = rnd(4, seed=2, dtype=torch.float32)
+    out, out_r = torch.zeros(2, 4, 64, 64, device=dev), torch.zeros(2, 4, 64, 64, device=dev)
+    ops.conv_out(x, w, b, out, 64, 64)
+    ref.conv_out(x, w, b, out_r, 64, 64)
+    assert_close(out, out_r, rel=1e-4, max_rel=1e-3, what="conv_out")
+    # upsample / im2col
+    x = rnd(2, 256, 640)
+    y, y_r = torch.zeros(2, 1024, 640, device=dev, dtype=torch.bfloat16), torch.zeros(2, 1024, 640, device=dev, dtype=torch.bfloat16)
+    ops.upsample2x(x, y, 16, 16); ref.upsample2x(x, y_r, 16, 16)
+    assert torch.equal(y, y_r)
+    col, col_r = torch.zeros(2 * 64, 9 * 640, device=dev, dtype=torch.bfloat16), torch.zeros(2 * 64, 9 * 640, device=dev, dtype=torch.bfloat16)
+    ops.im2col_s2(x, col, 16, 16); ref.im2col_s2(x, col_r, 16, 16)
+    assert torch.equal(col, col_r)
+    # timestep embedding
+    t = torch.tensor([981, 1, 500, 21], device=dev)
+    o, o_r = torch.zeros(4, 320, device=dev, dtype=torch.bfloat16), torch.zeros(4, 320, device=dev, dtype=torch.bfloat16)
+    ops.timestep_embedding(t, o); ref.timestep_embedding(t, o_r)
+    assert_close(o, o_r, rel=4e-3, max_rel=1e-2, what="timestep_embedding")
+    # position features (text: F=768, 4 coords; keypoint: broadcast table, 2 coords, padded K)
+    for F_, nc, ldo, bc in ((768, 4, 832, False), (768, 2, 832, True)):
+        B, N = 3, 30
+        feat = rnd(N, F_, dtype=torch.float32) if bc else rnd(B, N, F_, dtype=torch.float32)
+        fm = (torch.rand(B, N, device=dev) > 0.4).float()
+        pm = (torch.rand(B, N, device=dev) > 0.4).float()
+        coords = torch.rand(B, N, nc, device=dev)
+        nf, npos = rnd(F_, seed=5, dtype=torch.float32), rnd(16 * nc, seed=6, dtype=torch.float32)
+        o, o_r = torch.ones(B * N, ldo, device=dev, dtype=torch.bfloat16), torch.ones(B * N, ldo, device=dev, dtype=torch.bfloat16)
+        ops.position_features(feat, fm, nf, coords, pm, npos, o, 8); ref.position_features(feat, fm, nf, coords, pm, npos, o_r, 8)
+        assert_close(o, o_r, rel=4e-3, max_rel=1e-2, what="position_features")
+    # cast
+    x = rnd(1000, 77, dtype=torch.float32)
+    y = torch.zeros(1000, 77, device=dev, dtype=torch.bfloat16)
+    ops.cast(x, y)
+    assert torch.equal(y, x.to(torch.bfloat16))
+    # sampler update
+    n = (4, 4, 64, 64)
+    xs, ec, eu, o1, o2, o3 = (rnd(*n, seed=s, dtype=torch.float32) for s in range(6))
+    for olds, coefs in (([], (1.0, 0, 0, 0)), ([o1], (1.5, -0.5, 0, 0)), ([o1, o2, o3], (55 / 24, -59 / 24, 37 / 24, -9 / 24))):
+        e, xp, e_r, xp_r = (torch.zeros(n, device=dev) for _ in range(4))
+        ops.sampler_update(xs, ec, eu, 7.5, olds, coefs, 0.5, 0.6, e, xp)
+        ref.sampler_update(xs, ec, eu, 7.5, olds, coefs, 0.5, 0.6, e_r, xp_r)
+        assert_close(e, e_r, rel=1e-5, max_rel=1e-4, what="sampler e")
+        assert_close(xp, xp_r, rel=1e-5, max_rel=1e-4, what="sampler x_prev")
+    torch.cuda.synchronize()
