@@ -25,19 +25,25 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
-// ---- GroupNorm pass 1: per-(batch, group) sum and sum of squares -------------------------------
+// ---- GroupNorm pass 1: per-(batch, group) mean / rstd, DETERMINISTIC ---------------------------------
 // grid (chunks, B); blockDim = (C/8) * rpi, thread -> (fixed channel vector cv, row lane rl).
-__global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ stats,
-                                int HW, int C, int groups, int rows_per_chunk) {
+// Each CTA writes its per-group partial (sum, sumsq) to scratch; the last CTA of a batch (atomic ticket)
+// reduces the partials in chunk order - no floating-point atomics on the result, so a forward is
+// bit-reproducible run to run.
+// scratch layout (floats): final[B][G][2] (sum, sumsq) | partial[B][chunks][G][2] | ticket[B] (uint)
+__global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ scratch,
+                                int B, int HW, int C, int groups, int rows_per_chunk) {
   extern __shared__ float gn_sm[];          // [2][C]
+  __shared__ bool is_last;
   float* s_sum = gn_sm;
   float* s_sq = gn_sm + C;
   const int vec = C >> 3;
   const int rpi = blockDim.x / vec;
   const int cv = threadIdx.x % vec, rl = threadIdx.x / vec;
-  const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) gn_sm[i] = 0.f;
-  __syncthreads();
+  const int b = blockIdx.y, chunks = gridDim.x;
+  float* fin = scratch + (long long)b * groups * 2;
+  float* part = scratch + (long long)B * groups * 2 + ((long long)b * chunks + blockIdx.x) * groups * 2;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + (long long)B * groups * 2 * (1 + chunks)) + b;
   const int r0 = blockIdx.x * rows_per_chunk;
   const int r1 = min(HW, r0 + rows_per_chunk);
   float a[8], q[8];
@@ -50,15 +56,37 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float
 #pragma unroll
     for (int j = 0; j < 8; ++j) { a[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
   }
+  // fixed-order reduction over the rpi row lanes: lane rl == k adds in turn
+  for (int k = 0; k < rpi; ++k) {
+    if (rl == k) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { atomicAdd(&s_sum[cv * 8 + j], a[j]); atomicAdd(&s_sq[cv * 8 + j], q[j]); }
-  __syncthreads();
+      for (int j = 0; j < 8; ++j) {
+        if (k == 0) { s_sum[cv * 8 + j] = a[j]; s_sq[cv * 8 + j] = q[j]; }
+        else { s_sum[cv * 8 + j] += a[j]; s_sq[cv * 8 + j] += q[j]; }
+      }
+    }
+    __syncthreads();
+  }
   const int cpg = C / groups;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     float s = 0.f, ss = 0.f;
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) { s += s_sum[c]; ss += s_sq[c]; }
-    atomicAdd(&stats[((long long)b * groups + g) * 2 + 0], s);
-    atomicAdd(&stats[((long long)b * groups + g) * 2 + 1], ss);
+    part[g * 2 + 0] = s;
+    part[g * 2 + 1] = ss;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == (unsigned)chunks - 1u);
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    const float* pb = scratch + (long long)B * groups * 2 + (long long)b * chunks * groups * 2;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+      float s = 0.f, ss = 0.f;
+      for (int k = 0; k < chunks; ++k) { s += __ldcg(pb + (long long)k * groups * 2 + g * 2); ss += __ldcg(pb + (long long)k * groups * 2 + g * 2 + 1); }
+      fin[g * 2] = s;
+      fin[g * 2 + 1] = ss;
+    }
   }
 }
 
@@ -162,8 +190,6 @@ extern "C" int glg_groupnorm(const void* x, int64_t ldx, void* y, int64_t ldy, c
   if (C % 8 || C % groups || (ldx % 8) || (ldy % 8)) return set_error("glg_groupnorm: C and leading dims must be multiples of 8, C % groups == 0");
   if (C > 4096) return set_error("glg_groupnorm: C too large");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(float) * 2 * B * groups, st);
-  if (e != cudaSuccess) return set_error(std::string("glg_groupnorm memset: ") + cudaGetErrorString(e));
   const int vec = C / 8;
   int rpi = 256 / vec; if (rpi < 1) rpi = 1;
   const int threads = vec * rpi;          // <= 512 for C <= 4096
@@ -175,7 +201,10 @@ extern "C" int glg_groupnorm(const void* x, int64_t ldx, void* y, int64_t ldy, c
   const int rows_per_chunk = (HW + chunks - 1) / chunks;
   chunks = (HW + rows_per_chunk - 1) / rows_per_chunk;
   dim3 grid(chunks, B);
-  gn_stats_kernel<<<grid, threads, 2 * C * sizeof(float), st>>>((const bf16*)x, ldx, stats, HW, C, groups, rows_per_chunk);
+  if ((long long)B * groups * 2 * (1 + chunks) + B > (long long)GLG_GN_SCRATCH_FLOATS(B, groups)) return set_error("glg_groupnorm: internal scratch sizing");
+  cudaError_t e = cudaMemsetAsync(stats + (long long)B * groups * 2 * (1 + chunks), 0, sizeof(unsigned int) * B, st);
+  if (e != cudaSuccess) return set_error(std::string("glg_groupnorm memset: ") + cudaGetErrorString(e));
+  gn_stats_kernel<<<grid, threads, 2 * C * sizeof(float), st>>>((const bf16*)x, ldx, stats, B, HW, C, groups, rows_per_chunk);
   count_launch();
   if (check_launch("gn_stats launch")) return -1;
   gn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), st>>>((const bf16*)x, ldx, (bf16*)y, ldy, gamma, beta, stats, HW, C, groups, eps, silu, rows_per_chunk);

@@ -37,6 +37,7 @@ class Plan:
         self.out: Optional[torch.Tensor] = None
         self.graphs: Dict[bool, object] = {}
         self.warm: Dict[bool, int] = {}
+        self.nlaunch: Dict[bool, int] = {}
 
     def add(self, name: str, fn: Callable[[], None], fuser: bool = False) -> None:
         self.steps.append((name, fuser, fn))
@@ -60,6 +61,7 @@ class Engine:
         self.scale = 1.0
         self.use_graphs = use_graphs and self.dev.type == "cuda"
         self.loaded = False
+        self.kernel_launches = 0       # kernels of libgligen_b200.so executed on behalf of this engine (graph replays included)
         # (prefix of every SpatialTransformer, in execution order) -> index into the gate table
         self.st_prefixes = [ly.prefix for blk in self.blocks for ly in blk.layers if ly.kind == "st"]
         self.res_layers = [ly for blk in self.blocks for ly in blk.layers if ly.kind == "res"]
@@ -251,7 +253,7 @@ class Engine:
         sz = self._sizes(Bt, N, nctx)
         B_ = {k: self._buf(v) for k, v in sz.items()}
         B_["blk2"] = self._buf(sz["blk"])
-        stats = self._buf(Bt * 32 * 2, torch.float32)
+        stats = self._buf(2 * 32 * (Bt + 4 * 148 + 2 * Bt) + Bt + 64, torch.float32)   # GLG_GN_SCRATCH_FLOATS
         Himg = cfg.image_size
         f32 = torch.float32
 
@@ -491,22 +493,23 @@ class Engine:
 
     def _execute(self, P: Plan) -> None:
         fuser_on = self.scale != 0.0
-        if not self.use_graphs:
+        ops = self.ops
+        if not self.use_graphs or P.graphs.get(fuser_on) is None and P.warm.get(fuser_on, 0) < 1:
+            # eager pass (also the first call of a shape: creates tensor maps, sets kernel attributes)
+            c0 = ops.launch_count()
             P.run(fuser_on)
+            P.nlaunch[fuser_on] = ops.launch_count() - c0
+            self.kernel_launches += P.nlaunch[fuser_on]
+            P.warm[fuser_on] = P.warm.get(fuser_on, 0) + 1
             return
         g = P.graphs.get(fuser_on)
         if g is None:
-            # first call runs eagerly (creates the tensor maps, sets kernel attributes), second captures
-            n = P.warm.get(fuser_on, 0)
-            if n < 1:
-                P.run(fuser_on)
-                P.warm[fuser_on] = n + 1
-                return
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 P.run(fuser_on)
             P.graphs[fuser_on] = g
         g.replay()
+        self.kernel_launches += P.nlaunch[fuser_on]
 
     @torch.no_grad()
     def forward(self, x, timesteps, context, grounding, inpainting_extra_input=None) -> torch.Tensor:

@@ -45,6 +45,11 @@ class CudaOps:
         if self.device.type != "cuda":
             raise L.GligenLibraryError("CudaOps needs a CUDA device (there is no CPU fallback)")
         self.lib = L.load()
+        self.trace = None          # set to a list to record (kind, algorithmic flops, algorithmic bytes) per op call
+
+    def _note(self, kind, flops=0.0, nbytes=0.0):
+        if self.trace is not None:
+            self.trace.append((kind, float(flops), float(nbytes)))
 
     # -- helpers --------------------------------------------------------------------------------
     def _stream(self):
@@ -90,6 +95,9 @@ class CudaOps:
         else:
             g.conv_mode, g.Bn, g.H, g.Wd = 0, 0, 0, 0
         L.check(self.lib.glg_gemm(C.byref(g), self._stream()), "glg_gemm")
+        taps = 9 if conv is not None else 1
+        self._note("conv3x3" if conv is not None else "gemm", 2.0 * M * N * K * taps,
+                   2.0 * (M * K + N * K * taps + M * No) + (2.0 * M * No if residual is not None else 0.0))
 
     # -- attention ---------------------------------------------------------------------------------
     def attention(self, q, k, v, out, heads: int, d_head: int):
@@ -105,6 +113,7 @@ class CudaOps:
         a.B, a.heads, a.d_head, a.Lq, a.Lk = B, heads, d_head, Lq, Lk
         a.scale = float(d_head) ** -0.5
         L.check(self.lib.glg_attention(C.byref(a), self._stream()), "glg_attention")
+        self._note("attention", 4.0 * B * heads * Lq * Lk * d_head, 2.0 * B * heads * d_head * (2 * Lq + 2 * Lk))
 
     # -- norms ---------------------------------------------------------------------------------------
     def groupnorm(self, x, y, gamma, beta, stats, groups: int, eps: float, silu: bool):
@@ -114,6 +123,7 @@ class CudaOps:
         yp, _, _, ldy = _rows_view(y)
         L.check(self.lib.glg_groupnorm(xp, ldx, yp, ldy, gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(),
                                        B, HW, Cc, groups, eps, 1 if silu else 0, self._stream()), "glg_groupnorm")
+        self._note("groupnorm", 0.0, 2.0 * B * HW * Cc * 3)
 
     def layernorm(self, x, y, gamma, beta, eps: float = 1e-5):
         """x [B, rows, C] with contiguous rows inside a batch; y likewise (batch strides may differ)."""
@@ -121,6 +131,7 @@ class CudaOps:
         assert x.stride(2) == 1 and x.stride(1) == Cc and y.stride(2) == 1 and y.stride(1) == Cc
         L.check(self.lib.glg_layernorm(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), gamma.data_ptr(), beta.data_ptr(),
                                        B, rows, Cc, eps, self._stream()), "glg_layernorm")
+        self._note("layernorm", 0.0, 2.0 * B * rows * Cc * 2)
 
     # -- small ops -----------------------------------------------------------------------------------
     def conv_in(self, x, extra, w, bias, out):
@@ -132,6 +143,7 @@ class CudaOps:
         op, _, Cout, ldo = _rows_view(out)
         L.check(self.lib.glg_conv_in(x.data_ptr(), C0, _ptr(extra), C1, w.data_ptr(), bias.data_ptr(), op, ldo,
                                      B, H, W, Cout, self._stream()), "glg_conv_in")
+        self._note("conv_in")
 
     def conv_out(self, x, w, bias, out, H: int, W: int):
         """x [B, HW, Cin] bf16 -> out [B, Cout, H, W] fp32."""
@@ -140,23 +152,27 @@ class CudaOps:
         assert out.is_contiguous() and out.dtype == torch.float32
         L.check(self.lib.glg_conv_out(xp, ldx, w.data_ptr(), bias.data_ptr(), out.data_ptr(), B, H, W, Cin, out.shape[1],
                                       self._stream()), "glg_conv_out")
+        self._note("conv_out")
 
     def upsample2x(self, x, y, H: int, W: int):
         B, _, Cc = x.shape
         xp, _, _, ldx = _rows_view(x)
         yp, _, _, ldy = _rows_view(y)
         L.check(self.lib.glg_upsample2x(xp, ldx, yp, ldy, B, H, W, Cc, self._stream()), "glg_upsample2x")
+        self._note("upsample2x")
 
     def im2col_s2(self, x, y, H: int, W: int):
         B, _, Cc = x.shape
         xp, _, _, ldx = _rows_view(x)
         assert y.is_contiguous()
         L.check(self.lib.glg_im2col_s2(xp, ldx, y.data_ptr(), B, H, W, Cc, self._stream()), "glg_im2col_s2")
+        self._note("im2col_s2")
 
     def timestep_embedding(self, t, out):
         assert t.dtype == torch.int64 and out.is_contiguous()
         L.check(self.lib.glg_timestep_embedding(t.data_ptr(), out.data_ptr(), out.shape[0], out.shape[1], self._stream()),
                 "glg_timestep_embedding")
+        self._note("timestep_embedding")
 
     def position_features(self, feat, feat_mask, null_feat, coords, pos_mask, null_pos, out, freqs: int):
         """feat [B,N,F] or [N,F] (broadcast) fp32; coords [B,N,nc]; out [B*N, ldo] bf16."""
@@ -169,11 +185,13 @@ class CudaOps:
         L.check(self.lib.glg_position_features(feat.data_ptr(), fbs, feat_mask.data_ptr(), null_feat.data_ptr(), coords.data_ptr(),
                                                pos_mask.data_ptr(), null_pos.data_ptr(), out.data_ptr(), out.shape[-1],
                                                B, N, F_, nc, freqs, self._stream()), "glg_position_features")
+        self._note("position_features")
 
     def cast(self, x, y):
         """fp32 -> activation dtype, contiguous."""
         assert x.is_contiguous() and y.is_contiguous() and x.dtype == torch.float32 and x.numel() == y.numel()
         L.check(self.lib.glg_cast_f32_bf16(x.data_ptr(), y.data_ptr(), x.numel(), self._stream()), "glg_cast_f32_bf16")
+        self._note("cast_f32_bf16")
 
     def sampler_update(self, x, e_cond, e_uncond, guidance, olds, coefs, a_t, a_prev, e_out, x_prev):
         o = list(olds) + [None] * (3 - len(olds))
@@ -184,3 +202,4 @@ class CudaOps:
                                             float(coefs[0]), float(coefs[1]), float(coefs[2]), float(coefs[3]),
                                             float(a_t), float(a_prev), _ptr(e_out), x_prev.data_ptr(), x.numel(), self._stream()),
                 "glg_sampler_update")
+        self._note("sampler_update")

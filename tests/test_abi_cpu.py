@@ -1,0 +1,112 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/gligen_b200.h declares
+(no compute calls - there is no GPU here); the drop-in surface and host logic behave like the reference's."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import GOLD, ROOT
+from gligen_b200.spec import NAMED_CONFIGS, unet_param_shapes
+
+
+def test_library_exports_every_declared_symbol():
+    from gligen_b200 import build, lib
+    path = build.build()
+    assert os.path.exists(path)
+    header = open(os.path.join(ROOT, "include", "gligen_b200.h")).read()
+    declared = set(re.findall(r"\b(glg_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(lib.SIGNATURES), declared ^ set(lib.SIGNATURES)
+    so = ctypes.CDLL(path)
+    for name in declared:
+        assert getattr(so, name) is not None
+    L = lib.load()
+    assert L.glg_abi_version() == 1
+    assert L.glg_launch_count() == 0
+
+
+def test_kernels_are_blackwell_native():
+    """SASS evidence: tcgen05.mma -> UTCHMMA, TMA -> UTMALDG, tcgen05.ld -> LDTM (B200_PROFILING.md)."""
+    import shutil
+    import subprocess
+    from gligen_b200 import build
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run(["cuobjdump", "-sass", build.build()], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+
+
+def _tiny_model():
+    from ldm.util import instantiate_from_config
+    return instantiate_from_config(dict(target="ldm.modules.diffusionmodules.openaimodel.UNetModel", params=dict(
+        image_size=16, in_channels=4, out_channels=4, model_channels=64, attention_resolutions=[4, 2, 1], num_res_blocks=2,
+        channel_mult=[1, 2, 4, 4], num_heads=8, transformer_depth=1, context_dim=128, fuser_type="gatedSA", use_checkpoint=True,
+        grounding_tokenizer=dict(target="ldm.modules.diffusionmodules.text_grounding_net.PositionNet", params=dict(in_dim=128, out_dim=128)))))
+
+
+def test_dropin_unet_surface():
+    from ldm.modules.attention import GatedCrossAttentionDense, GatedSelfAttentionDense
+    from gligen_b200.spec import synthetic_state_dict
+    m = _tiny_model().eval()
+    ref = unet_param_shapes(NAMED_CONFIGS["tiny"])
+    sd = m.state_dict()
+    assert set(sd) == set(ref) and all(tuple(sd[k].shape) == tuple(ref[k]) for k in ref)
+    m.load_state_dict(synthetic_state_dict(NAMED_CONFIGS["tiny"], 0), strict=True)
+    fusers = [x for x in m.modules() if type(x) == GatedSelfAttentionDense or type(x) == GatedCrossAttentionDense]
+    assert len(fusers) == 16 and all(f.scale == 1 for f in fusers)
+    assert m.input_blocks[0][0].weight.shape == (64, 4, 3, 3)
+    assert (m.image_size, m.in_channels, m.inpaint_mode, m.first_conv_type, m.grounding_tokenizer_input) == (16, 4, False, "SD", None)
+    # fails loudly without a CUDA device: no CPU fallback on the product path
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(dict(x=torch.zeros(1, 4, 16, 16), timesteps=torch.zeros(1, dtype=torch.long), context=torch.zeros(1, 77, 128),
+               grounding_input=dict(boxes=torch.zeros(1, 2, 4), masks=torch.zeros(1, 2), positive_embeddings=torch.zeros(1, 2, 128))))
+    with pytest.raises(NotImplementedError):
+        from ldm.modules.diffusionmodules.openaimodel import UNetModel
+        UNetModel(16, 4, 64, 4, 2, [1], fuser_type="gatedCA", context_dim=128, grounding_tokenizer=dict(target="x"))
+
+
+def test_restore_first_conv_reads_cwd_relative_file(tmp_path, monkeypatch):
+    from ldm.util import instantiate_from_config
+    m = instantiate_from_config(dict(target="ldm.modules.diffusionmodules.openaimodel.UNetModel", params=dict(
+        image_size=8, in_channels=4, out_channels=4, model_channels=320, attention_resolutions=[], num_res_blocks=1,
+        channel_mult=[1], num_heads=8, context_dim=64, fuser_type="gatedSA",
+        grounding_tokenizer=dict(target="ldm.modules.diffusionmodules.text_grounding_net.PositionNet", params=dict(in_dim=64, out_dim=64)))))
+    monkeypatch.chdir(GOLD)
+    m.restore_first_conv_from_SD()
+    w = torch.load(os.path.join(GOLD, "SD_input_conv_weight_bias.pth"))
+    assert torch.equal(m.input_blocks[0][0].weight, w["weight"]) and torch.equal(m.input_blocks[0][0].bias, w["bias"])
+    assert abs(w["weight"].sum().item() - 1.770429) < 1e-4 and abs(w["bias"].sum().item() - 1.551949) < 1e-4
+    assert "weight" in m.GLIGEN_first_conv_state_dict and m.first_conv_type == "SD"
+
+
+def test_host_schedule_and_adapters():
+    import importlib
+    from inpaint_mask_func import draw_masks_from_boxes
+    from ldm.models.diffusion.ldm import LatentDiffusion
+    from ldm.models.diffusion.plms import PLMSSampler
+    from oracle import sampler_oracle as SO
+    a = torch.load(os.path.join(GOLD, "scalar_anchors.pt"))
+    d = LatentDiffusion(linear_start=0.00085, linear_end=0.012, timesteps=1000)
+    assert torch.equal(d.alphas_cumprod, a["alphas_cumprod"]) and d.num_timesteps == 1000
+    s = PLMSSampler(d, None)
+    s.make_schedule(50)
+    assert list(s.ddim_timesteps[:3]) == [1, 21, 41] and s.ddim_timesteps[-1] == 981
+    assert torch.allclose(torch.as_tensor(s.ddim_alphas), a["ddim50_alphas"]) and float(s.ddim_sigmas.max()) == 0.0
+    torch.manual_seed(0)
+    x0, t = torch.randn(2, 4, 8, 8), torch.tensor([981, 1])
+    torch.manual_seed(1); q1 = d.q_sample(x0, t)
+    torch.manual_seed(1); q2 = SO.q_sample(SO.make_schedule(), x0, t)
+    assert torch.equal(q1, q2)
+    boxes = torch.tensor([[[0.1, 0.2, 0.5, 0.9], [0.0, 0.0, 0.0, 0.0]], [[0.26, 0.51, 0.99, 1.0], [0.3, 0.3, 0.31, 0.31]]])
+    assert torch.equal(draw_masks_from_boxes(boxes, 64), SO.draw_masks_from_boxes(boxes, 64))
+    for mod, batch in (("text_grounding_tokinzer_input", dict(boxes=torch.rand(2, 5, 4), masks=torch.ones(2, 5), text_embeddings=torch.randn(2, 5, 8))),
+                       ("keypoint_grounding_tokinzer_input", dict(points=torch.rand(2, 34, 2), masks=torch.ones(2, 34)))):
+        g = importlib.import_module(f"grounding_input.{mod}").GroundingNetInput()
+        with pytest.raises(AssertionError):
+            g.get_null_input()
+        out = g.prepare(batch)
+        null = g.get_null_input()
+        assert set(null) == set(out) and all(null[k].shape == out[k].shape and null[k].abs().sum() == 0 for k in out)
+        assert g.get_null_input(batch=3)[next(iter(out))].shape[0] == 3

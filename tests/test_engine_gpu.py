@@ -108,6 +108,20 @@ def test_forward_tiny(name, gold_file):
     run_forwards(name, gold_file)
 
 
+class cpu_rng_noise:
+    """The golden latents come from a CPU run of the reference, whose randn_like / q_sample noise is drawn from
+    the CPU generator.  To compare on the GPU, draw the same noise in the same order from the CPU generator
+    (only matters for inpainting, where q_sample noise enters the result; sigma_t == 0 elsewhere)."""
+
+    def __enter__(self):
+        self.orig = torch.randn_like
+        torch.randn_like = lambda x, **kw: torch.randn(x.shape, dtype=x.dtype).to(x.device)
+        return self
+
+    def __exit__(self, *a):
+        torch.randn_like = self.orig
+
+
 def run_sampling(name, gold_file, kinds=("plms", "ddim")):
     from ldm.models.diffusion.ddim import DDIMSampler
     from ldm.models.diffusion.ldm import LatentDiffusion
@@ -128,7 +142,8 @@ def run_sampling(name, gold_file, kinds=("plms", "ddim")):
                          inpainting_extra_input=extra, grounding_extra_input=None)
             shape = (gold["B"], cfg.in_channels, cfg.image_size, cfg.image_size)
             torch.manual_seed(1234)
-            lat = sampler.sample(S=g["S"], shape=shape, input=input, uc=inp["uc"].to(DEV), guidance_scale=g["guidance"], mask=mask, x0=z0)
+            with cpu_rng_noise():
+                lat = sampler.sample(S=g["S"], shape=shape, input=input, uc=inp["uc"].to(DEV), guidance_scale=g["guidance"], mask=mask, x0=z0)
             r, m = assert_close(lat, g["latent"], rel=6e-2, max_rel=0.2, what=f"{name} {kind} S={g['S']} latent")
             print(f"{name} {kind} S={g['S']} alpha={g['alpha_type']}: latent rel_l2={r:.3e} max_rel={m:.3e}")
     finally:
@@ -168,4 +183,4 @@ def test_scale_zero_equals_fuser_removed():
     model.load_state_dict(sd)
     set_alpha_scale(model, 1.0)
     e1 = model(dict(x=x, timesteps=ts, context=ctx, grounding_input=grounding, inpainting_extra_input=None, grounding_extra_input=None))
-    assert rel_l2(e0, e1) < 1e-6
+    assert torch.equal(e0, e1), rel_l2(e0, e1)      # every kernel is deterministic: bit-identical

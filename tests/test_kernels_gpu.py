@@ -165,12 +165,15 @@ def test_groupnorm(ops, ref, B, HW, C, ld, eps, silu):
     x = big[:, :, ld - C:]
     gamma = 1 + 0.1 * rnd(C, seed=1, dtype=torch.float32)
     beta = 0.1 * rnd(C, seed=2, dtype=torch.float32)
-    stats = torch.zeros(B * 32 * 2, device="cuda:0")
+    stats = torch.zeros(2 * 32 * (B + 4 * 148 + 2 * B) + B + 64, device="cuda:0")
     y, y_r = torch.zeros(B, HW, C, device="cuda:0", dtype=torch.bfloat16), torch.zeros(B, HW, C, device="cuda:0", dtype=torch.bfloat16)
     ops.groupnorm(x, y, gamma, beta, stats, 32, eps, silu)
     torch.cuda.synchronize()
     ref.groupnorm(x, y_r, gamma, beta, stats, 32, eps, silu)
     assert_close(y, y_r, what="groupnorm")
+    y2 = torch.zeros_like(y)
+    ops.groupnorm(x, y2, gamma, beta, stats, 32, eps, silu)
+    assert torch.equal(y, y2), "groupnorm must be bit-reproducible"
 
 
 @pytest.mark.parametrize("B,rows,C", [(2, 4096, 320), (2, 30, 640), (3, 64, 1280), (2, 16, 64), (2, 7, 2048)])
@@ -207,7 +210,7 @@ def test_small_ops(ops, ref):
     out, out_r = torch.zeros(2, 4, 64, 64, device=dev), torch.zeros(2, 4, 64, 64, device=dev)
     ops.conv_out(x, w, b, out, 64, 64)
     ref.conv_out(x, w, b, out_r, 64, 64)
-    assert_close(out, out_r, rel=1e-4, max_rel=1e-3, what="conv_out")
+    assert_close(out, out_r, rel=2e-3, max_rel=5e-3, what="conv_out")   # torch reference conv runs in TF32
     # upsample / im2col
     x = rnd(2, 256, 640)
     y, y_r = torch.zeros(2, 1024, 640, device=dev, dtype=torch.bfloat16), torch.zeros(2, 1024, 640, device=dev, dtype=torch.bfloat16)

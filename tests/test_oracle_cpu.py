@@ -1,0 +1,101 @@
+"""CPU: the oracle restatement against the golden vectors written from the REAL reference
+(oracle/gen_golden.py), plus closed-form anchors."""
+import os
+
+import pytest
+import torch
+
+from conftest import GOLD
+from gligen_b200 import synth
+from gligen_b200.spec import NAMED_CONFIGS, flops_per_forward, synthetic_state_dict, unet_param_shapes
+from oracle import sampler_oracle as SO
+from oracle import unet_oracle as UO
+
+TINY = [("tiny", "tiny_B2_G6.pt"), ("tiny_text_image", "tiny_text_image_B2_G5.pt"),
+        ("tiny_keypoint", "tiny_keypoint_B2_G34.pt"), ("tiny_inpaint", "tiny_inpaint_B2_G6.pt")]
+
+
+def _case(name, gold):
+    cfg = NAMED_CONFIGS[name]
+    sd = synthetic_state_dict(cfg, 0)
+    inp = synth.make_inputs(cfg, gold["B"], gold["max_objs"], seed=2, n_valid=gold.get("n_valid"))
+    extra = mask = z0 = None
+    if cfg.inpaint_mode:
+        mask = SO.draw_masks_from_boxes(inp["batch"]["boxes"], cfg.image_size)
+        z0 = inp["z0"]
+        extra = torch.cat([z0 * mask, mask], dim=1)
+    return cfg, sd, inp, extra, mask, z0
+
+
+@pytest.mark.parametrize("name,gold_file", TINY)
+def test_oracle_forward_matches_reference(name, gold_file):
+    gold = torch.load(os.path.join(GOLD, gold_file))
+    cfg, sd, inp, extra, _, _ = _case(name, gold)
+    for scale, g in gold["forward"].items():
+        e_c = UO.unet_forward(cfg, sd, inp["x"], gold["timesteps"], inp["context"], inp["grounding_input"], scale, extra)
+        e_u = UO.unet_forward(cfg, sd, inp["x"], gold["timesteps"], inp["uc"], UO.null_grounding(cfg, inp["grounding_input"]), scale, extra)
+        assert (e_c - g["eps_cond"]).abs().max() < 2e-5
+        assert (e_u - g["eps_null"]).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("name,gold_file", TINY)
+@pytest.mark.parametrize("kind", ["plms", "ddim"])
+def test_oracle_sampling_matches_reference(name, gold_file, kind):
+    gold = torch.load(os.path.join(GOLD, gold_file))
+    cfg, sd, inp, extra, mask, z0 = _case(name, gold)
+    g = gold[kind]
+    state = {"scale": 1.0}
+
+    def eps_fn(x, t, cond):
+        gr = inp["grounding_input"] if cond else UO.null_grounding(cfg, inp["grounding_input"])
+        return UO.unet_forward(cfg, sd, x, t, inp["context"] if cond else inp["uc"], gr, state["scale"], extra)
+
+    fn = SO.plms_sample if kind == "plms" else SO.ddim_sample
+    torch.manual_seed(1234)
+    shape = (gold["B"], cfg.in_channels, cfg.image_size, cfg.image_size)
+    lat = fn(eps_fn, g["S"], shape, x_T=inp["x"].clone(), guidance_scale=g["guidance"],
+             alphas=SO.alpha_generator(g["S"], g["alpha_type"]), on_alpha=lambda a: state.update(scale=a), mask=mask, x0=z0)
+    assert (lat - g["latent"]).abs().max() < 5e-4
+
+
+def test_scalar_anchors():
+    a = torch.load(os.path.join(GOLD, "scalar_anchors.pt"))
+    te = UO.timestep_embedding(torch.tensor([981, 1]), 320)
+    assert torch.allclose(te, a["timestep_embedding_981_1"], atol=1e-6)
+    assert abs(te[0, 0].item() - 0.67995721) < 1e-6 and abs(te[0, 160].item() - 0.73325181) < 1e-6
+    fe = UO.fourier_embed(torch.tensor([[0.25, 0.5, 0.75, 1.0]]), 8)
+    assert torch.allclose(fe, a["fourier_box"], atol=1e-6)
+    assert torch.allclose(fe[0, :8], torch.tensor([0.24740396, 0.47942555, 0.68163878, 0.84147096, 0.96891242, 0.87758255, 0.73168886, 0.54030234]), atol=1e-6)
+    sched = SO.make_schedule()
+    assert torch.equal(sched["alphas_cumprod"], a["alphas_cumprod"])
+    assert abs(sched["alphas_cumprod"][0].item() - 0.99914998) < 1e-7 and abs(sched["alphas_cumprod"][999].item() - 0.00466010) < 1e-7
+    _, al, alp = SO.ddim_parameters(sched["alphas_cumprod"], SO.ddim_timesteps(50))
+    assert abs(float(al[0]) - 0.99829602) < 1e-7 and abs(float(al[-1]) - 0.00577550) < 1e-7 and abs(float(alp[-1]) - 0.00728173) < 1e-7
+    assert SO.alpha_generator(50, [0.3, 0.0, 0.7]) == [1] * 15 + [0] * 35
+
+
+def test_spec_inventory_and_flops():
+    cfg = NAMED_CONFIGS["sd14_box_text"]
+    shapes = unet_param_shapes(cfg)
+    assert len(shapes) == 966
+    n = sum(int(torch.Size(s).numel()) for s in shapes.values())
+    assert n == 1068623204                                            # 1068.6 M (SURVEY 2b probe)
+    assert abs(flops_per_forward(cfg, 30) / 1e9 - 1136.9) < 0.1
+    assert abs(flops_per_forward(cfg, 30, False) / 1e9 - 803.3) < 0.1
+    assert abs(flops_per_forward(cfg, 2) / 1e9 - 1130.9) < 0.1
+    assert abs(flops_per_forward(NAMED_CONFIGS["sd14_keypoint"], 136) / 1e9 - 1160.3) < 0.1
+
+
+def test_fresh_init_invariants():
+    """Design invariants of the reference: zeroed out-conv => eps == 0; scale=0 == alphas=0."""
+    cfg = NAMED_CONFIGS["tiny"]
+    sd = synthetic_state_dict(cfg, 0)
+    inp = synth.make_inputs(cfg, 1, 4, seed=3)
+    ts = torch.tensor([500])
+    z = dict(sd)
+    z["out.2.weight"], z["out.2.bias"] = torch.zeros_like(sd["out.2.weight"]), torch.zeros_like(sd["out.2.bias"])
+    assert UO.unet_forward(cfg, z, inp["x"], ts, inp["context"], inp["grounding_input"]).abs().max() == 0
+    a0 = {k: (torch.zeros(()) if k.endswith(("alpha_attn", "alpha_dense")) else v) for k, v in sd.items()}
+    e0 = UO.unet_forward(cfg, sd, inp["x"], ts, inp["context"], inp["grounding_input"], 0.0)
+    e1 = UO.unet_forward(cfg, a0, inp["x"], ts, inp["context"], inp["grounding_input"], 1.0)
+    assert torch.equal(e0, e1)
