@@ -249,7 +249,14 @@ static int launch_attn(const AttnKParams& p, int B, cudaStream_t st) {
 
 }  // namespace glg
 
+namespace glg {
+int attention_tc(const GlgAttnArgs* a, cudaStream_t st);   // attention_tc.cu: tcgen05 path for d_head <= 64
+int g_attn_mode = 0;                                       // 0 = auto, 1 = force the mma.sync kernel (test hook)
+}
+
 using namespace glg;
+
+extern "C" void glg_debug_attn_mode(int mode) { glg::g_attn_mode = mode; }
 
 extern "C" int glg_attention(const GlgAttnArgs* a, void* stream) {
   if (!a) return set_error("glg_attention: null args");
@@ -258,6 +265,10 @@ extern "C" int glg_attention(const GlgAttnArgs* a, void* stream) {
   if ((a->q_row | a->k_row | a->v_row | a->q_batch | a->k_batch | a->v_batch) % 8) return set_error("glg_attention: q/k/v strides must be multiples of 8 elements");
   if ((a->o_row | a->o_batch) % 2) return set_error("glg_attention: output strides must be even");
   if (((uintptr_t)a->q | (uintptr_t)a->k | (uintptr_t)a->v) & 15) return set_error("glg_attention: q/k/v must be 16-byte aligned");
+  if (g_attn_mode == 0) {
+    const int rc = attention_tc(a, reinterpret_cast<cudaStream_t>(stream));
+    if (rc <= 0) return rc;          // 0 = launched, -1 = error; 1 = not applicable -> mma.sync kernel below
+  }
   AttnKParams p;
   p.q = (const bf16*)a->q; p.k = (const bf16*)a->k; p.v = (const bf16*)a->v; p.o = (bf16*)a->out;
   p.q_row = a->q_row; p.k_row = a->k_row; p.v_row = a->v_row; p.o_row = a->o_row;

@@ -1,0 +1,292 @@
+// tcgen05 / TMEM flash attention for head dims <= 64 (the 64x64-latent level, d_head = 40, carries 88 % of
+// the attention FLOPs).
+//
+//   per CTA: one (batch, head, 128-query tile); key/value tiles of 64 keys stream through a TMA ring.
+//   warp 0 lane 0 : TMA producer (Q once, then K_j / V_j tiles; 4-D tensor maps {d, head, row, batch},
+//                   box {64, 1, rows, 1}: columns >= d and rows >= L are zero-filled by TMA)
+//   warp 1 lane 0 : MMA issuer   S_j = Q K_j^T          (SS: both operands K-major in smem, N = 64)
+//                                O  += P_j V_j           (TS: P_j bf16 in TMEM, V_j MN-major in smem)
+//   warps 2..5    : softmax      thread == query row: tcgen05.ld S_j -> running max (lazy rescale of O only
+//                                when the max grows by > 2^8) -> exp2 -> P_j bf16 -> tcgen05.st
+//   TMEM (256 columns): S[2] (2 x 64 fp32) | P[2] (2 x 32 packed bf16) | O (<= 64 fp32).  S and P are double
+//   buffered so QK^T of tile j+1 overlaps the softmax of tile j; two CTAs are resident per SM so the
+//   exp2 (MUFU) pipe - the real bound at d = 40 - stays busy while the other CTA waits on its MMAs.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string>
+
+#include "common.cuh"
+#include "internal.h"
+#include "../../include/gligen_b200.h"
+
+namespace glg {
+
+struct AttnTcParams {
+  bf16* o; long long o_row, o_batch;
+  int heads, d, Lq, Lk;
+  float scale_log2;
+};
+
+namespace atc {
+constexpr int BM = 128, BN = 64;
+constexpr int Q_BYTES = BM * 64 * 2;        // 16 KB
+constexpr int KV_BYTES = BN * 64 * 2;       // 8 KB each for K and V
+constexpr int STAGES = 4;
+constexpr int SMEM_BYTES = Q_BYTES + STAGES * 2 * KV_BYTES + 1024 + 256;
+constexpr int TMEM_COLS = 256;
+constexpr int S_COL = 0, P_COL = 128, O_COL = 192;
+constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
+}  // namespace atc
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int DPAD>   // head dim rounded up to a multiple of 16 (<= 64)
+__global__ void __launch_bounds__(192, 2)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+  using namespace atc;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base;
+  const uint32_t sKV = base + Q_BYTES;
+  const uint32_t bar_base = sKV + STAGES * 2 * KV_BYTES;
+  const uint32_t q_full = bar_base;
+  auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bar_base + 8u * (1 + STAGES + s); };
+  auto s_full = [&](int b) { return bar_base + 8u * (1 + 2 * STAGES + b); };
+  auto p_full = [&](int b) { return bar_base + 8u * (3 + 2 * STAGES + b); };
+  auto pv_done = [&](int b) { return bar_base + 8u * (5 + 2 * STAGES + b); };
+  const uint32_t o_full = bar_base + 8u * (7 + 2 * STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (8 + 2 * STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BM;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int nkt = (p.Lk + BN - 1) / BN;
+
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(s_full(i), 1); mbar_init(p_full(i), 128); mbar_init(pv_done(i), 1); }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    if (lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    mbar_arrive_expect_tx(q_full, Q_BYTES);
+    tma_load_4d(sQ, &tmQ, q_full, 0, h, q0, b);
+    int stage = 0; uint32_t phase = 0;
+    for (int j = 0; j < nkt; ++j) {
+      mbar_wait(kv_empty(stage), phase ^ 1u);
+      mbar_arrive_expect_tx(kv_full(stage), 2 * KV_BYTES);
+      tma_load_4d(sKV + stage * 2 * KV_BYTES, &tmK, kv_full(stage), 0, h, j * BN, b);
+      tma_load_4d(sKV + stage * 2 * KV_BYTES + KV_BYTES, &tmV, kv_full(stage), 0, h, j * BN, b);
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, BN);            // S = Q K^T : N = 64 keys
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, DPAD, true);    // O += P V  : N = DPAD, B (V) is MN-major
+    const uint64_t qdesc = umma_desc_kmajor_sw128(sQ);
+    mbar_wait(q_full, 0);
+    tc_fence_after();
+    auto issue_qk = [&](int j) {
+      const int stage = j % STAGES;
+      mbar_wait(kv_full(stage), (uint32_t)((j / STAGES) & 1));
+      tc_fence_after();
+      const uint64_t kdesc = umma_desc_kmajor_sw128(sKV + stage * 2 * KV_BYTES);
+      const uint32_t d_tmem = tmem_base + S_COL + (j & 1) * BN;
+#pragma unroll
+      for (int k = 0; k < DPAD / 16; ++k) umma_bf16(d_tmem, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+      umma_commit(s_full(j & 1));
+    };
+    issue_qk(0);
+    for (int j = 0; j < nkt; ++j) {
+      if (j + 1 < nkt) issue_qk(j + 1);           // S buffer (j+1)&1 is free: P_{j-1} was consumed before PV_{j-1} issued
+      const int stage = j % STAGES, bsel = j & 1;
+      mbar_wait(p_full(bsel), (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      const uint64_t vdesc = umma_desc_mnmajor_sw128(sKV + stage * 2 * KV_BYTES + KV_BYTES);
+      const uint32_t a_tmem = tmem_base + P_COL + bsel * (BN / 2);
+#pragma unroll
+      for (int k = 0; k < BN / 16; ++k)           // 16 keys per step: +8 TMEM columns of P, +16 rows (2048 B) of V
+        umma_bf16_ts(tmem_base + O_COL, a_tmem + 8 * k, vdesc + 128 * k, idesc_o, (j | k) != 0 ? 1u : 0u);
+      umma_commit(kv_empty(stage));
+      umma_commit(pv_done(bsel));
+    }
+    umma_commit(o_full);
+  } else if (warp >= 2) {
+    // ===================== softmax / correction / output =====================
+    const int q = warp & 3;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int row = q0 + q * 32 + lane;
+    const float sl2 = p.scale_log2;
+    float m_ref = -INFINITY;        // reference max (raw score units) the stored P / O are relative to
+    float l = 0.f;
+    for (int j = 0; j < nkt; ++j) {
+      const int bsel = j & 1;
+      mbar_wait(s_full(bsel), (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      uint32_t s0[32], s1[32];
+      tmem_ld32(lane_base + S_COL + bsel * BN, s0);
+      tmem_ld32(lane_base + S_COL + bsel * BN + 32, s1);
+      tmem_ld_wait();
+      if (j == nkt - 1 && (p.Lk & (BN - 1))) {
+        const int valid = p.Lk - j * BN;         // keys [valid, 64) are padding
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i >= valid) s0[i] = 0xff800000u;   // -inf
+          if (i + 32 >= valid) s1[i] = 0xff800000u;
+        }
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
+      // O (and the P buffer about to be overwritten) are stable once PV_{j-1} has completed
+      if (j > 0) {
+        mbar_wait(pv_done(bsel ^ 1), (uint32_t)(((j - 1) >> 1) & 1));
+        tc_fence_after();
+      }
+      const float m_new = fmaxf(m_ref, mx);
+      if (j == 0) {
+        m_ref = m_new;
+      } else {
+        const bool need = (m_new - m_ref) * sl2 > RESCALE_THRESHOLD;
+        if (__any_sync(0xffffffffu, need)) {     // tcgen05.ld/st are warp-collective: whole warp rescales
+          const float f = need ? ex2_approx((m_ref - m_new) * sl2) : 1.0f;
+          if (need) { m_ref = m_new; l *= f; }
+#pragma unroll
+          for (int c = 0; c < DPAD / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld16(lane_base + O_COL + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st16(lane_base + O_COL + c * 16, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float ms = m_ref * sl2;
+      uint32_t pk[32];
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float a0 = ex2_approx(fmaf(__uint_as_float(s0[2 * i]), sl2, -ms));
+        const float a1 = ex2_approx(fmaf(__uint_as_float(s0[2 * i + 1]), sl2, -ms));
+        const float b0 = ex2_approx(fmaf(__uint_as_float(s1[2 * i]), sl2, -ms));
+        const float b1 = ex2_approx(fmaf(__uint_as_float(s1[2 * i + 1]), sl2, -ms));
+        sum += (a0 + a1) + (b0 + b1);
+        pk[i] = pack_bf16x2(a0, a1);
+        pk[16 + i] = pack_bf16x2(b0, b1);
+      }
+      l += sum;
+      tmem_st32(lane_base + P_COL + bsel * (BN / 2), pk);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full(bsel));
+    }
+    // ---- epilogue: O / l -> bf16
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    bf16* orow = p.o + (long long)b * p.o_batch + (long long)row * p.o_row + (long long)h * p.d;
+#pragma unroll
+    for (int c = 0; c < DPAD / 16; ++c) {
+      uint32_t o[16];
+      tmem_ld16(lane_base + O_COL + c * 16, o);
+      tmem_ld_wait();
+      if (row < p.Lq) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int col = c * 16 + g * 8;
+          if (col < p.d) {           // d is a multiple of 8: whole 8-column groups are valid or not
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + col) = u;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, atc::TMEM_COLS);
+  }
+}
+
+template <int DPAD>
+static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p, int B, cudaStream_t st) {
+  static bool attr_set = false;
+  auto kern = attn_tc_kernel<DPAD>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(attn_tc): ") + cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((p.Lq + atc::BM - 1) / atc::BM, p.heads, B);
+  kern<<<grid, 192, atc::SMEM_BYTES, st>>>(tq, tk, tv, p);
+  count_launch();
+  return check_launch("attention_tc launch");
+}
+
+// Returns 1 if this path does not apply (caller falls back to the mma.sync kernel), 0 on success, -1 on error.
+int attention_tc(const GlgAttnArgs* a, cudaStream_t st) {
+  if (a->d_head > 64) return 1;
+  // tensor-map constraints: 16-byte aligned bases and strides; the output is written with 16-byte stores
+  if ((a->d_head % 8) || (a->o_row % 8) || (a->o_batch % 8) || ((uintptr_t)a->out & 15)) return 1;
+  CUtensorMap tq, tk, tv;
+  const uint64_t d = a->d_head, hd = a->heads;
+  {
+    const uint64_t dims[4] = {d, hd, (uint64_t)a->Lq, (uint64_t)a->B};
+    const uint64_t str[3] = {d * 2, (uint64_t)a->q_row * 2, (uint64_t)a->q_batch * 2};
+    const uint32_t box[4] = {64, 1, (uint32_t)atc::BM, 1};
+    if (get_tmap_bf16(&tq, a->q, 4, dims, str, box)) return -1;
+  }
+  {
+    const uint64_t dims[4] = {d, hd, (uint64_t)a->Lk, (uint64_t)a->B};
+    const uint64_t strk[3] = {d * 2, (uint64_t)a->k_row * 2, (uint64_t)a->k_batch * 2};
+    const uint64_t strv[3] = {d * 2, (uint64_t)a->v_row * 2, (uint64_t)a->v_batch * 2};
+    const uint32_t box[4] = {64, 1, (uint32_t)atc::BN, 1};
+    if (get_tmap_bf16(&tk, a->k, 4, dims, strk, box)) return -1;
+    if (get_tmap_bf16(&tv, a->v, 4, dims, strv, box)) return -1;
+  }
+  AttnTcParams p;
+  p.o = (bf16*)a->out; p.o_row = a->o_row; p.o_batch = a->o_batch;
+  p.heads = a->heads; p.d = a->d_head; p.Lq = a->Lq; p.Lk = a->Lk;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  const int dpad = (a->d_head + 15) / 16 * 16;
+  switch (dpad) {
+    case 16: return launch_attn_tc<16>(tq, tk, tv, p, a->B, st);
+    case 32: return launch_attn_tc<32>(tq, tk, tv, p, a->B, st);
+    case 48: return launch_attn_tc<48>(tq, tk, tv, p, a->B, st);
+    case 64: return launch_attn_tc<64>(tq, tk, tv, p, a->B, st);
+  }
+  return 1;
+}
+
+}  // namespace glg

@@ -283,8 +283,8 @@ static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
 static std::mutex g_tmap_mu;
 
 // bf16 tensor map, 128B swizzle, zero OOB fill.  dims/strides innermost first; strides in bytes (rank-1 of them).
-static int get_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
-                    const uint32_t* box) {
+int get_tmap_bf16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
+                  const uint32_t* box) {
   TmapKey key;
   memset(&key, 0, sizeof(key));
   key.ptr = ptr; key.rank = rank;
@@ -317,7 +317,7 @@ static int get_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t*
 }
 
 static int g_num_sms = 0;
-static int num_sms() {
+int num_sms() {
   if (!g_num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -414,20 +414,20 @@ extern "C" int glg_gemm(const GlgGemmArgs* a, void* stream) {
     p.HW = HW; p.Wd = W;
     const uint64_t dims[4] = {(uint64_t)a->K, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t str[3] = {(uint64_t)a->lda * 2, (uint64_t)a->lda * 2 * W, (uint64_t)a->lda * 2 * HW};
-    if (get_tmap(&ta, a->A, 4, dims, str, box)) return -1;
+    if (get_tmap_bf16(&ta, a->A, 4, dims, str, box)) return -1;
     const uint64_t wd[2] = {(uint64_t)a->K, (uint64_t)a->N * 9};
     const uint64_t ws[1] = {(uint64_t)a->K * 2};
     const uint32_t wb[2] = {64, (uint32_t)bn};
-    if (get_tmap(&tb, a->W, 2, wd, ws, wb)) return -1;
+    if (get_tmap_bf16(&tb, a->W, 2, wd, ws, wb)) return -1;
   } else {
     const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
     const uint64_t str[1] = {(uint64_t)a->lda * 2};
     const uint32_t box[2] = {64, 128};
-    if (get_tmap(&ta, a->A, 2, dims, str, box)) return -1;
+    if (get_tmap_bf16(&ta, a->A, 2, dims, str, box)) return -1;
     const uint64_t wd[2] = {(uint64_t)a->K, (uint64_t)a->N};
     const uint64_t ws[1] = {(uint64_t)a->K * 2};
     const uint32_t wb[2] = {64, (uint32_t)bn};
-    if (get_tmap(&tb, a->W, 2, wd, ws, wb)) return -1;
+    if (get_tmap_bf16(&tb, a->W, 2, wd, ws, wb)) return -1;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (a->geglu) return launch_gemm<256, true>(ta, tb, p, st);

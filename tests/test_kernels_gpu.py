@@ -130,11 +130,18 @@ ATTN_CASES = [
     (2, 8, 16, 64, 70, "fuser"),
     (2, 8, 32, 16, 22, "fuser"),
     (2, 4, 64, 200, 333, "plain"),
+    (1, 2, 40, 128, 64, "plain"),
+    (1, 2, 40, 128, 8192, "plain"),
+    (8, 8, 40, 4096, 4126, "fuser"),
 ]
 
 
 @pytest.mark.parametrize("B,heads,d,Lq,Lk,mode", ATTN_CASES)
-def test_attention(ops, ref, B, heads, d, Lq, Lk, mode):
+@pytest.mark.parametrize("path", ["auto", "mma_sync"])
+def test_attention(ops, ref, B, heads, d, Lq, Lk, mode, path):
+    """path=auto: tcgen05/TMEM kernel for d_head <= 64, mma.sync kernel above; path=mma_sync forces the latter."""
+    if path == "mma_sync" and d > 64:
+        pytest.skip("same kernel as auto")
     C = heads * d
     if mode == "qkv":
         qkv = rnd(B, Lk, 3 * C)
@@ -150,8 +157,12 @@ def test_attention(ops, ref, B, heads, d, Lq, Lk, mode):
         q, k, v = rnd(B, Lq, C), rnd(B, Lk, C, seed=1), rnd(B, Lk, C, seed=2)
     out = torch.zeros(B, Lq, C, device="cuda:0", dtype=torch.bfloat16)
     out_r = torch.zeros_like(out)
-    ops.attention(q, k, v, out, heads, d)
-    torch.cuda.synchronize()
+    ops.lib.glg_debug_attn_mode(1 if path == "mma_sync" else 0)
+    try:
+        ops.attention(q, k, v, out, heads, d)
+        torch.cuda.synchronize()
+    finally:
+        ops.lib.glg_debug_attn_mode(0)
     ref.attention(q, k, v, out_r, heads, d)
     assert_close(out, out_r, rel=1e-2, max_rel=5e-2, what=f"attention d={d} {Lq}x{Lk} {mode}")
 
