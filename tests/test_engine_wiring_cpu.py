@@ -37,8 +37,10 @@ def test_engine_plan_matches_reference(name, gold_file):
             assert (got - ref).abs().max() < 5e-5
     # the fuser steps are really skipped at scale 0 (launch accounting)
     P = next(iter(eng.plans.values()))
-    n_fuser = sum(1 for _, fu, _ in P.steps if fu)
+    n_fuser = sum(1 for _, fu, st, _ in P.steps if fu)
     assert n_fuser == 16 * (8 + eng.n_streams)
+    n_static = sum(1 for _, fu, st, _ in P.steps if st)
+    assert n_static == 4 * eng.n_streams + 1 + 2 * 16          # PositionNet, context cast, attn2.kv + fuser.linear per block
 
 
 def test_first_conv_swap_is_in_place():
