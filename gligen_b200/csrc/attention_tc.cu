@@ -6,8 +6,11 @@
 //                   box {64, 1, rows, 1}: columns >= d and rows >= L are zero-filled by TMA)
 //   warp 1 lane 0 : MMA issuer   S_j = Q K_j^T          (SS: both operands K-major in smem, N = 64)
 //                                O  += P_j V_j           (TS: P_j bf16 in TMEM, V_j MN-major in smem)
-//   warps 2..5    : softmax      thread == query row: tcgen05.ld S_j -> running max (lazy rescale of O only
-//                                when the max grows by > 2^8) -> exp2 -> P_j bf16 -> tcgen05.st
+//   warps 2..9    : softmax      two threads per query row (32 of the tile's 64 keys each; partial row maxima
+//                                are exchanged through smem): tcgen05.ld S_j -> running max (lazy rescale of
+//                                O only when the max grows by > 2^8) -> exp2 -> P_j bf16 -> tcgen05.st.
+//                                8 warps x 2 resident CTAs = 4 softmax warps per SM sub-partition, so TMEM
+//                                reads (64 B/clk/SM) and exp2 (16/clk/SM) - equal cost per score - overlap.
 //   TMEM (256 columns): S[2] (2 x 64 fp32) | P[2] (2 x 32 packed bf16) | O (<= 64 fp32).  S and P are double
 //   buffered so QK^T of tile j+1 overlaps the softmax of tile j; two CTAs are resident per SM so the
 //   exp2 (MUFU) pipe - the real bound at d = 40 - stays busy while the other CTA waits on its MMAs.
@@ -33,7 +36,8 @@ constexpr int BM = 128, BN = 64;
 constexpr int Q_BYTES = BM * 64 * 2;        // 16 KB
 constexpr int KV_BYTES = BN * 64 * 2;       // 8 KB each for K and V
 constexpr int STAGES = 4;
-constexpr int SMEM_BYTES = Q_BYTES + STAGES * 2 * KV_BYTES + 1024 + 256;
+constexpr int XCH_BYTES = 2 * 2 * 128 * 4;   // [parity][column half][row] partial maxima / sums
+constexpr int SMEM_BYTES = Q_BYTES + STAGES * 2 * KV_BYTES + 1024 + 256 + XCH_BYTES;
 constexpr int TMEM_COLS = 256;
 constexpr int S_COL = 0, P_COL = 128, O_COL = 192;
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
@@ -46,7 +50,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 template <int DPAD>   // head dim rounded up to a multiple of 16 (<= 64)
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(320, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
   using namespace atc;
@@ -63,6 +67,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   auto pv_done = [&](int b) { return bar_base + 8u * (5 + 2 * STAGES + b); };
   const uint32_t o_full = bar_base + 8u * (7 + 2 * STAGES);
   const uint32_t tmem_slot = bar_base + 8u * (8 + 2 * STAGES);
+  const uint32_t xch = bar_base + 256;          // float [2][2][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BM;
@@ -72,7 +77,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(s_full(i), 1); mbar_init(p_full(i), 128); mbar_init(pv_done(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(s_full(i), 1); mbar_init(p_full(i), 256); mbar_init(pv_done(i), 1); }
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -134,31 +139,38 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     umma_commit(o_full);
   } else if (warp >= 2) {
     // ===================== softmax / correction / output =====================
-    const int q = warp & 3;
+    const int q = warp & 3;                      // TMEM lane quarter
+    const int hc = (warp - 2) >> 2;              // column half of the key tile this thread owns
+    const int rloc = q * 32 + lane;              // row inside the 128-query tile
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int row = q0 + q * 32 + lane;
+    const int row = q0 + rloc;
     const float sl2 = p.scale_log2;
+    auto xch_addr = [&](int par, int half, int r) { return xch + (uint32_t)(((par * 2 + half) * 128 + r) * 4); };
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
     float m_ref = -INFINITY;        // reference max (raw score units) the stored P / O are relative to
-    float l = 0.f;
+    float l = 0.f;                  // this thread's partial row sum (its 32 keys per tile)
     for (int j = 0; j < nkt; ++j) {
       const int bsel = j & 1;
       mbar_wait(s_full(bsel), (uint32_t)((j >> 1) & 1));
       tc_fence_after();
-      uint32_t s0[32], s1[32];
-      tmem_ld32(lane_base + S_COL + bsel * BN, s0);
-      tmem_ld32(lane_base + S_COL + bsel * BN + 32, s1);
+      uint32_t sv[32];
+      tmem_ld32(lane_base + S_COL + bsel * BN + hc * 32, sv);
       tmem_ld_wait();
       if (j == nkt - 1 && (p.Lk & (BN - 1))) {
-        const int valid = p.Lk - j * BN;         // keys [valid, 64) are padding
+        const int valid = p.Lk - j * BN - hc * 32;      // keys [valid, 32) of this half are padding
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i >= valid) s0[i] = 0xff800000u;   // -inf
-          if (i + 32 >= valid) s1[i] = 0xff800000u;
-        }
+        for (int i = 0; i < 32; ++i)
+          if (i >= valid) sv[i] = 0xff800000u;          // -inf
       }
       float mx = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+      // row max = max over both column halves: exchange through smem with the partner warp (same rows)
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch_addr(bsel, hc, rloc)), "f"(mx) : "memory");
+      pair_sync();
+      float other;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch_addr(bsel, hc ^ 1, rloc)) : "memory");
+      mx = fmaxf(mx, other);
       // O (and the P buffer about to be overwritten) are stable once PV_{j-1} has completed
       if (j > 0) {
         mbar_wait(pv_done(bsel ^ 1), (uint32_t)(((j - 1) >> 1) & 1));
@@ -174,6 +186,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           if (need) { m_ref = m_new; l *= f; }
 #pragma unroll
           for (int c = 0; c < DPAD / 16; ++c) {
+            if ((c & 1) != hc) continue;         // the two warps of a lane quarter split the O columns
             uint32_t o[16];
             tmem_ld16(lane_base + O_COL + c * 16, o);
             tmem_ld_wait();
@@ -185,31 +198,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
       }
       const float ms = m_ref * sl2;
-      uint32_t pk[32];
+      uint32_t pk[16];
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float a0 = ex2_approx(fmaf(__uint_as_float(s0[2 * i]), sl2, -ms));
-        const float a1 = ex2_approx(fmaf(__uint_as_float(s0[2 * i + 1]), sl2, -ms));
-        const float b0 = ex2_approx(fmaf(__uint_as_float(s1[2 * i]), sl2, -ms));
-        const float b1 = ex2_approx(fmaf(__uint_as_float(s1[2 * i + 1]), sl2, -ms));
-        sum += (a0 + a1) + (b0 + b1);
+        const float a0 = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), sl2, -ms));
+        const float a1 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -ms));
+        sum += a0 + a1;
         pk[i] = pack_bf16x2(a0, a1);
-        pk[16 + i] = pack_bf16x2(b0, b1);
       }
       l += sum;
-      tmem_st32(lane_base + P_COL + bsel * (BN / 2), pk);
+      tmem_st16(lane_base + P_COL + bsel * (BN / 2) + hc * 16, pk);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_full(bsel));
     }
-    // ---- epilogue: O / l -> bf16
+    // ---- epilogue: total row sum, O / l -> bf16
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch_addr(nkt & 1, hc, rloc)), "f"(l) : "memory");
+    pair_sync();
+    float l_other;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l_other) : "r"(xch_addr(nkt & 1, hc ^ 1, rloc)) : "memory");
     mbar_wait(o_full, 0);
     tc_fence_after();
-    const float inv = 1.0f / l;
+    const float inv = 1.0f / (l + l_other);
     bf16* orow = p.o + (long long)b * p.o_batch + (long long)row * p.o_row + (long long)h * p.d;
 #pragma unroll
     for (int c = 0; c < DPAD / 16; ++c) {
+      if ((c & 1) != hc) continue;
       uint32_t o[16];
       tmem_ld16(lane_base + O_COL + c * 16, o);
       tmem_ld_wait();
@@ -249,7 +264,7 @@ static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CU
     attr_set = true;
   }
   dim3 grid((p.Lq + atc::BM - 1) / atc::BM, p.heads, B);
-  kern<<<grid, 192, atc::SMEM_BYTES, st>>>(tq, tk, tv, p);
+  kern<<<grid, 320, atc::SMEM_BYTES, st>>>(tq, tk, tv, p);
   count_launch();
   return check_launch("attention_tc launch");
 }

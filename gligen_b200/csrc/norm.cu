@@ -91,40 +91,81 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float
 }
 
 // ---- GroupNorm pass 2: normalise + affine (+SiLU) -----------------------------------------------
+// Same thread -> (channel vector, row lane) mapping as pass 1: the 8 scale/shift pairs of a thread live in
+// registers, the row loop is a pure 16-byte load / 8 FMA (+SiLU) / 16-byte store stream.
 __global__ void gn_apply_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ stats, int HW, int C, int groups, float eps, int silu,
                                 int rows_per_chunk) {
-  extern __shared__ float gn_sm[];          // scale[C], shift[C]
-  float* s_a = gn_sm;
-  float* s_b = gn_sm + C;
+  const int vec = C >> 3;
+  const int rpi = blockDim.x / vec;
+  const int cv = threadIdx.x % vec, rl = threadIdx.x / vec;
   const int b = blockIdx.y;
   const int cpg = C / groups;
   const float inv_n = 1.f / ((float)HW * (float)cpg);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  float sa[8], sb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cv * 8 + j;
     const int g = c / cpg;
     const float mean = stats[((long long)b * groups + g) * 2] * inv_n;
     const float var = fmaxf(stats[((long long)b * groups + g) * 2 + 1] * inv_n - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + eps);
-    const float ga = gamma[c] * rstd;
-    s_a[c] = ga;
-    s_b[c] = beta[c] - mean * ga;
+    const float ga = gamma[c] * rsqrtf(var + eps);
+    sa[j] = ga;
+    sb[j] = beta[c] - mean * ga;
   }
-  __syncthreads();
-  const int vec = C >> 3;
   const int r0 = blockIdx.x * rows_per_chunk;
   const int r1 = min(HW, r0 + rows_per_chunk);
-  const long long total = (long long)(r1 - r0) * vec;
-  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
-    const int r = r0 + (int)(i / vec), cv = (int)(i % vec);
+  const bf16* xb = x + (long long)b * HW * ldx + cv * 8;
+  bf16* yb = y + (long long)b * HW * ldy + cv * 8;
+  for (int r = r0 + rl; r < r1; r += rpi) {
     float v[8];
-    load8(x + ((long long)b * HW + r) * ldx + cv * 8, v);
+    load8(xb + (long long)r * ldx, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float t = fmaf(v[j], s_a[cv * 8 + j], s_b[cv * 8 + j]);
+      const float t = fmaf(v[j], sa[j], sb[j]);
       v[j] = silu ? silu_f(t) : t;
     }
-    store8(y + ((long long)b * HW + r) * ldy + cv * 8, v);
+    store8(yb + (long long)r * ldy, v);
+  }
+}
+
+// ---- small tensors: ONE kernel, one CTA per (group, batch): stats + apply, deterministic -------------
+// Used when H*W <= 256 (the 16x16 / 8x8 levels): the three-launch path above is launch/latency bound there.
+__global__ void gn_small_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                int HW, int C, int groups, float eps, int silu) {
+  __shared__ float red[2][32];
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int cpg = C / groups, half = cpg >> 1;        // cpg is even: process bf16 pairs
+  const int total = HW * half;
+  const bf16* xb = x + (long long)b * HW * ldx + g * cpg;
+  bf16* yb = y + (long long)b * HW * ldy + g * cpg;
+  float s = 0.f, ss = 0.f;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int r = i / half, c2 = i - r * half;
+    const float2 f = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(xb + (long long)r * ldx + c2 * 2)));
+    s += f.x + f.y;
+    ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss));
+  }
+  s = warp_sum(s); ss = warp_sum(ss);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (lane == 0) { red[0][warp] = s; red[1][warp] = ss; }
+  __syncthreads();
+  float ts = 0.f, tss = 0.f;
+  for (int w = 0; w < nw; ++w) { ts += red[0][w]; tss += red[1][w]; }      // fixed order: deterministic
+  const float inv_n = 1.f / (float)(HW * cpg);
+  const float mean = ts * inv_n;
+  const float rstd = rsqrtf(fmaxf(tss * inv_n - mean * mean, 0.f) + eps);
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int r = i / half, c2 = i - r * half;
+    const int c = g * cpg + c2 * 2;
+    const float2 f = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(xb + (long long)r * ldx + c2 * 2)));
+    const float g0 = gamma[c] * rstd, g1 = gamma[c + 1] * rstd;
+    float t0 = fmaf(f.x, g0, beta[c] - mean * g0);
+    float t1 = fmaf(f.y, g1, beta[c + 1] - mean * g1);
+    if (silu) { t0 = silu_f(t0); t1 = silu_f(t1); }
+    *reinterpret_cast<uint32_t*>(yb + (long long)r * ldy + c2 * 2) = pack_bf16x2(t0, t1);
   }
 }
 
@@ -190,6 +231,12 @@ extern "C" int glg_groupnorm(const void* x, int64_t ldx, void* y, int64_t ldy, c
   if (C % 8 || C % groups || (ldx % 8) || (ldy % 8)) return set_error("glg_groupnorm: C and leading dims must be multiples of 8, C % groups == 0");
   if (C > 4096) return set_error("glg_groupnorm: C too large");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (HW <= 256 && ((C / groups) % 2 == 0)) {
+    dim3 grid(groups, B);
+    gn_small_kernel<<<grid, 256, 0, st>>>((const bf16*)x, ldx, (bf16*)y, ldy, gamma, beta, HW, C, groups, eps, silu);
+    count_launch();
+    return check_launch("gn_small launch");
+  }
   const int vec = C / 8;
   int rpi = 256 / vec; if (rpi < 1) rpi = 1;
   const int threads = vec * rpi;          // <= 512 for C <= 4096
@@ -207,7 +254,7 @@ extern "C" int glg_groupnorm(const void* x, int64_t ldx, void* y, int64_t ldy, c
   gn_stats_kernel<<<grid, threads, 2 * C * sizeof(float), st>>>((const bf16*)x, ldx, stats, B, HW, C, groups, rows_per_chunk);
   count_launch();
   if (check_launch("gn_stats launch")) return -1;
-  gn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), st>>>((const bf16*)x, ldx, (bf16*)y, ldy, gamma, beta, stats, HW, C, groups, eps, silu, rows_per_chunk);
+  gn_apply_kernel<<<grid, threads, 0, st>>>((const bf16*)x, ldx, (bf16*)y, ldy, gamma, beta, stats, HW, C, groups, eps, silu, rows_per_chunk);
   count_launch();
   return check_launch("gn_apply launch");
 }

@@ -7,7 +7,7 @@ nvidia-smi --query-gpu=name,driver_version,memory.total,clocks.max.sm --format=c
 run() {
   name=$1; shift
   echo "=== $name" | tee -a gpurun_out/summary.txt
-  timeout 900 python -m pytest "$@" -q -m gpu --timeout 600 -s > gpurun_out/$name.log 2>&1
+  timeout 1500 python -m pytest "$@" -q -m gpu --timeout 1200 -s > gpurun_out/$name.log 2>&1
   echo "exit $?" >> gpurun_out/$name.log
   tail -n 3 gpurun_out/$name.log | tee -a gpurun_out/summary.txt
 }
