@@ -49,7 +49,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int DPAD>   // head dim rounded up to a multiple of 16 (<= 64)
+// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, 2^f by an own degree-3
+// fit (max rel. error 7.5e-5, well below the bf16 rounding of P), exponent patched in with integer adds.
+// Used for every POLY-th probability so the MUFU pipe (16 exp2/clk/SM, the bound at d_head = 40) is relieved.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -120.0f);
+  const float t = x + 12582912.0f;               // 1.5 * 2^23: integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  float pl = fmaf(0.0551716685295105f, f, 0.2426111251115799f);
+  pl = fmaf(pl, f, 0.6932609677314758f);
+  pl = fmaf(pl, f, 0.9999280571937561f);
+  return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
+}
+
+template <int DPAD, int POLY>   // DPAD: head dim rounded up to a multiple of 16 (<= 64); POLY: 0 = all MUFU, k = every k-th via ex2_poly
 __global__ void __launch_bounds__(320, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
@@ -202,8 +215,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float a0 = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), sl2, -ms));
-        const float a1 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -ms));
+        const float x0 = fmaf(__uint_as_float(sv[2 * i]), sl2, -ms);
+        const float x1 = fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -ms);
+        const float a0 = ex2_approx(x0);
+        const float a1 = (POLY != 0 && ((2 * i + 1) % (POLY ? POLY : 1)) == POLY - 1) ? ex2_poly(x1) : ex2_approx(x1);
         sum += a0 + a1;
         pk[i] = pack_bf16x2(a0, a1);
       }
@@ -254,10 +269,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
-template <int DPAD>
-static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p, int B, cudaStream_t st) {
+int g_attn_poly = 4;   // every 4th exp2 on the FMA pipe (test hook: glg_debug_attn_poly)
+
+template <int DPAD, int POLY>
+static int launch_attn_tc2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p, int B, cudaStream_t st) {
   static bool attr_set = false;
-  auto kern = attn_tc_kernel<DPAD>;
+  auto kern = attn_tc_kernel<DPAD, POLY>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(attn_tc): ") + cudaGetErrorString(e));
@@ -267,6 +284,15 @@ static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CU
   kern<<<grid, 320, atc::SMEM_BYTES, st>>>(tq, tk, tv, p);
   count_launch();
   return check_launch("attention_tc launch");
+}
+
+template <int DPAD>
+static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p, int B, cudaStream_t st) {
+  switch (g_attn_poly) {
+    case 0: return launch_attn_tc2<DPAD, 0>(tq, tk, tv, p, B, st);
+    case 2: return launch_attn_tc2<DPAD, 2>(tq, tk, tv, p, B, st);
+    default: return launch_attn_tc2<DPAD, 4>(tq, tk, tv, p, B, st);
+  }
 }
 
 // Returns 1 if this path does not apply (caller falls back to the mma.sync kernel), 0 on success, -1 on error.
@@ -305,3 +331,5 @@ int attention_tc(const GlgAttnArgs* a, cudaStream_t st) {
 }
 
 }  // namespace glg
+
+extern "C" void glg_debug_attn_poly(int k) { glg::g_attn_poly = k; }

@@ -35,6 +35,12 @@ struct GemmKParams {
   void* out; long long ldc; int out_fp32;
   const float* bias; const float* rowbias; long long ld_rowbias; int rows_per_batch;
   int act; const float* gate; const bf16* residual; long long ldr;
+  // LayerNorm fold (consumer side): per-row partial (sum, sumsq) of A over K, column sums of the weights
+  const float* ln_stats; int ln_slots; const float* ln_colsum; float ln_eps; float inv_k;
+  // producer side: per-row partial (sum, sumsq) of the bf16 values this GEMM stores
+  float* stats_out; int stats_slots;
+  // batch-strided output rows: address = (row / orpb) * obs + (row % orpb) * ldc   (orpb == 0: uniform rows)
+  int orpb; long long obs;
 };
 
 template <int BN> struct GemmCfg {
@@ -162,6 +168,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int row = m_blk * 128 + q * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      // LayerNorm fold: y = rstd * (acc - mu * colsum[n]) + bias'[n]   (gamma folded into W, beta into bias')
+      float ln_mu = 0.f, ln_rstd = 1.f;
+      if (p.ln_stats && row_ok) {
+        const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + (size_t)row * p.ln_slots;
+        float s1 = 0.f, s2 = 0.f;
+        for (int i = 0; i < p.ln_slots; ++i) { const float2 t = __ldg(sp + i); s1 += t.x; s2 += t.y; }   // fixed order
+        ln_mu = s1 * p.inv_k;
+        ln_rstd = rsqrtf(fmaxf(s2 * p.inv_k - ln_mu * ln_mu, 0.f) + p.ln_eps);
+      }
+      const size_t out_off = p.orpb ? (size_t)(row / p.orpb) * p.obs + (size_t)(row % p.orpb) * p.ldc : (size_t)row * p.ldc;
+      float st_sum = 0.f, st_sq = 0.f;
       if constexpr (GEGLU) {
         constexpr int HALF = BN / 2;
         constexpr int NCH = HALF / 32;
@@ -174,6 +191,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float v[32];
           const float* bx = p.bias + (size_t)n_blk * BN + c * 32;
           const float* bg = bx + HALF;
+          if (p.ln_stats) {
+            const float* sx = p.ln_colsum + (size_t)n_blk * BN + c * 32;
+            const float* sg = sx + HALF;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 ux = __ldg(reinterpret_cast<const float4*>(sx + j));
+              const float4 ug = __ldg(reinterpret_cast<const float4*>(sg + j));
+              rx[j + 0] = __float_as_uint(ln_rstd * (__uint_as_float(rx[j + 0]) - ln_mu * ux.x));
+              rx[j + 1] = __float_as_uint(ln_rstd * (__uint_as_float(rx[j + 1]) - ln_mu * ux.y));
+              rx[j + 2] = __float_as_uint(ln_rstd * (__uint_as_float(rx[j + 2]) - ln_mu * ux.z));
+              rx[j + 3] = __float_as_uint(ln_rstd * (__uint_as_float(rx[j + 3]) - ln_mu * ux.w));
+              rg[j + 0] = __float_as_uint(ln_rstd * (__uint_as_float(rg[j + 0]) - ln_mu * ug.x));
+              rg[j + 1] = __float_as_uint(ln_rstd * (__uint_as_float(rg[j + 1]) - ln_mu * ug.y));
+              rg[j + 2] = __float_as_uint(ln_rstd * (__uint_as_float(rg[j + 2]) - ln_mu * ug.z));
+              rg[j + 3] = __float_as_uint(ln_rstd * (__uint_as_float(rg[j + 3]) - ln_mu * ug.w));
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 tx = __ldg(reinterpret_cast<const float4*>(bx + j));
@@ -183,7 +217,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             v[j + 2] = (__uint_as_float(rx[j + 2]) + tx.z) * gelu_erf_f(__uint_as_float(rg[j + 2]) + tg.z);
             v[j + 3] = (__uint_as_float(rx[j + 3]) + tx.w) * gelu_erf_f(__uint_as_float(rg[j + 3]) + tg.w);
           }
-          if (row_ok) epi_store_bf16(reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldc + (size_t)n_blk * HALF + c * 32, v);
+          if (row_ok) epi_store_bf16(reinterpret_cast<bf16*>(p.out) + out_off + (size_t)n_blk * HALF + c * 32, v);
         }
       } else {
         const float* rb = (p.rowbias && row_ok) ? p.rowbias + (size_t)(row / p.rows_per_batch) * p.ld_rowbias : nullptr;
@@ -197,6 +231,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.ln_stats) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + j));
+              v[j] = ln_rstd * (v[j] - ln_mu * t.x); v[j + 1] = ln_rstd * (v[j + 1] - ln_mu * t.y);
+              v[j + 2] = ln_rstd * (v[j + 2] - ln_mu * t.z); v[j + 3] = ln_rstd * (v[j + 3] - ln_mu * t.w);
+            }
+          }
           if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -233,14 +275,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
             if (p.out_fp32) {
-              float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)row * p.ldc + n0);
+              float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + n0);
 #pragma unroll
               for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             } else {
-              epi_store_bf16(reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldc + n0, v);
+              if (p.stats_out) {      // statistics of the values as stored (bf16-rounded): what the consumer GEMM will read
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const float rv = __bfloat162float(__float2bfloat16(v[j]));
+                  st_sum += rv; st_sq = fmaf(rv, rv, st_sq);
+                }
+              }
+              epi_store_bf16(reinterpret_cast<bf16*>(p.out) + out_off + n0, v);
             }
           }
         }
+      }
+      if (p.stats_out && row_ok) {
+        float2* so = reinterpret_cast<float2*>(p.stats_out) + (size_t)row * p.stats_slots;
+        so[n_blk * 2 + half] = make_float2(st_sum, st_sq);
+        if (n_blk == 0 && half == 0)
+          for (int i = 2 * p.tiles_n; i < p.stats_slots; ++i) so[i] = make_float2(0.f, 0.f);
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
@@ -406,6 +461,21 @@ extern "C" int glg_gemm(const GlgGemmArgs* a, void* stream) {
   p.out = a->out; p.ldc = a->ldc; p.out_fp32 = a->out_fp32;
   p.bias = a->bias; p.rowbias = a->rowbias; p.ld_rowbias = a->ld_rowbias; p.rows_per_batch = a->rows_per_batch > 0 ? a->rows_per_batch : 1;
   p.act = a->act; p.gate = a->gate; p.residual = reinterpret_cast<const bf16*>(a->residual); p.ldr = a->ldr;
+  if (a->ln_stats) {
+    if (!a->ln_colsum || a->ln_slots <= 0 || a->conv_mode) return set_error("glg_gemm: LayerNorm fold needs ln_colsum, ln_slots > 0 and a plain GEMM");
+    if (((uintptr_t)a->ln_stats & 7) || ((uintptr_t)a->ln_colsum & 15)) return set_error("glg_gemm: ln_stats / ln_colsum alignment");
+    p.ln_stats = a->ln_stats; p.ln_slots = a->ln_slots; p.ln_colsum = a->ln_colsum; p.ln_eps = a->ln_eps; p.inv_k = 1.0f / (float)a->K;
+  }
+  if (a->stats_out) {
+    if (a->geglu || a->out_fp32 || 2 * p.tiles_n > a->stats_slots || ((uintptr_t)a->stats_out & 7))
+      return set_error("glg_gemm: stats_out needs a bf16 non-GEGLU output and stats_slots >= 2 * ceil(N / tile)");
+    p.stats_out = a->stats_out; p.stats_slots = a->stats_slots;
+  }
+  if (a->out_rows_per_batch > 0) {
+    if (a->out_batch_stride % 8) return set_error("glg_gemm: out_batch_stride must be a multiple of 8");
+    p.orpb = a->out_rows_per_batch; p.obs = a->out_batch_stride;
+  }
+  if (a->bias && ((uintptr_t)a->bias & 15)) return set_error("glg_gemm: bias must be 16-byte aligned");
 
   CUtensorMap ta, tb;
   if (a->conv_mode) {

@@ -10,6 +10,13 @@
 
 namespace glg {
 
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  float2 f;
+  f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+  f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+  f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+  f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+}
 __device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
   const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
   float2 f;
@@ -50,7 +57,20 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a[j] = 0.f; q[j] = 0.f; }
   const bf16* xb = x + (long long)b * HW * ldx + cv * 8;
-  for (int r = r0 + rl; r < r1; r += rpi) {
+  int r = r0 + rl;
+  for (; r + 3 * rpi < r1; r += 4 * rpi) {      // 4 independent 16-byte loads in flight per thread
+    uint4 u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u[i] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)(r + i * rpi) * ldx));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float v[8];
+      unpack8(u[i], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+    }
+  }
+  for (; r < r1; r += rpi) {
     float v[8];
     load8(xb + (long long)r * ldx, v);
 #pragma unroll
@@ -118,7 +138,24 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, long long ldx, bf16*
   const int r1 = min(HW, r0 + rows_per_chunk);
   const bf16* xb = x + (long long)b * HW * ldx + cv * 8;
   bf16* yb = y + (long long)b * HW * ldy + cv * 8;
-  for (int r = r0 + rl; r < r1; r += rpi) {
+  int r = r0 + rl;
+  for (; r + 3 * rpi < r1; r += 4 * rpi) {
+    uint4 u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u[i] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)(r + i * rpi) * ldx));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float v[8];
+      unpack8(u[i], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = fmaf(v[j], sa[j], sb[j]);
+        v[j] = silu ? silu_f(t) : t;
+      }
+      store8(yb + (long long)(r + i * rpi) * ldy, v);
+    }
+  }
+  for (; r < r1; r += rpi) {
     float v[8];
     load8(xb + (long long)r * ldx, v);
 #pragma unroll

@@ -89,13 +89,28 @@ class Engine:
         return t.detach().to(device=self.dev, dtype=torch.float32).contiguous()
 
     @staticmethod
-    def _pack_geglu(w: torch.Tensor, b: torch.Tensor):
-        """[x rows | gate rows] -> per 256-row tile [128 x | 128 gate] (glg_gemm geglu layout)."""
+    def _pack_geglu(w: torch.Tensor, *vecs: torch.Tensor):
+        """[x rows | gate rows] -> per 256-row tile [128 x | 128 gate] (glg_gemm geglu layout); per-row vectors
+        (bias, column sums) are permuted the same way."""
         n2 = w.shape[0] // 2
         assert n2 % 128 == 0, "GEGLU inner dim must be a multiple of 128"
         wx, wg = w[:n2].reshape(n2 // 128, 128, -1), w[n2:].reshape(n2 // 128, 128, -1)
-        bx, bg = b[:n2].reshape(n2 // 128, 128), b[n2:].reshape(n2 // 128, 128)
-        return torch.stack([wx, wg], dim=1).reshape(2 * n2, -1), torch.stack([bx, bg], dim=1).reshape(2 * n2)
+        out = [torch.stack([wx, wg], dim=1).reshape(2 * n2, -1)]
+        for b in vecs:
+            bx, bg = b[:n2].reshape(n2 // 128, 128), b[n2:].reshape(n2 // 128, 128)
+            out.append(torch.stack([bx, bg], dim=1).reshape(2 * n2))
+        return out
+
+    def _fold_ln(self, w: torch.Tensor, bias, gamma: torch.Tensor, beta: torch.Tensor):
+        """LayerNorm(gamma, beta) followed by Linear(w, bias)  ->  (w * gamma in the activation dtype,
+        column sums of THAT rounded matrix, bias + w @ beta), all still in the reference row order."""
+        w32 = w.float()
+        wf = (w32 * gamma.float()[None, :]).to(self.adt)
+        colsum = wf.float().sum(dim=1)
+        b = w32 @ beta.float()
+        if bias is not None:
+            b = b + bias.float()
+        return wf, colsum, b
 
     @staticmethod
     def _pack_conv3(w: torch.Tensor) -> torch.Tensor:
@@ -137,18 +152,22 @@ class Engine:
                     W[f"{p}.proj_in.w"], W[f"{p}.proj_in.b"] = self._a(sd[f"{p}.proj_in.weight"].reshape(C, C)), self._f(sd[f"{p}.proj_in.bias"])
                     W[f"{p}.proj_out.w"], W[f"{p}.proj_out.b"] = self._a(sd[f"{p}.proj_out.weight"].reshape(C, C)), self._f(sd[f"{p}.proj_out.bias"])
                     tb = f"{p}.transformer_blocks.0"
-                    for a in ("attn1", "fuser.attn"):
-                        W[f"{tb}.{a}.qkv.w"] = self._a(torch.cat([sd[f"{tb}.{a}.to_q.weight"], sd[f"{tb}.{a}.to_k.weight"], sd[f"{tb}.{a}.to_v.weight"]], dim=0))
+                    # every LayerNorm -> Linear pair is folded (see include/gligen_b200.h "LayerNorm fold")
+                    for a, nrm in (("attn1", "norm1"), ("fuser.attn", "fuser.norm1")):
+                        wq = torch.cat([sd[f"{tb}.{a}.to_q.weight"], sd[f"{tb}.{a}.to_k.weight"], sd[f"{tb}.{a}.to_v.weight"]], dim=0)
+                        wf, cs, b = self._fold_ln(wq, None, sd[f"{tb}.{nrm}.weight"], sd[f"{tb}.{nrm}.bias"])
+                        W[f"{tb}.{a}.qkv.w"], W[f"{tb}.{a}.qkv.s"], W[f"{tb}.{a}.qkv.b"] = wf.to(self.dev).contiguous(), self._f(cs), self._f(b)
                         W[f"{tb}.{a}.out.w"], W[f"{tb}.{a}.out.b"] = self._a(sd[f"{tb}.{a}.to_out.0.weight"]), self._f(sd[f"{tb}.{a}.to_out.0.bias"])
-                    W[f"{tb}.attn2.q.w"] = self._a(sd[f"{tb}.attn2.to_q.weight"])
+                    wf, cs, b = self._fold_ln(sd[f"{tb}.attn2.to_q.weight"], None, sd[f"{tb}.norm2.weight"], sd[f"{tb}.norm2.bias"])
+                    W[f"{tb}.attn2.q.w"], W[f"{tb}.attn2.q.s"], W[f"{tb}.attn2.q.b"] = wf.to(self.dev).contiguous(), self._f(cs), self._f(b)
                     W[f"{tb}.attn2.kv.w"] = self._a(torch.cat([sd[f"{tb}.attn2.to_k.weight"], sd[f"{tb}.attn2.to_v.weight"]], dim=0))
                     W[f"{tb}.attn2.out.w"], W[f"{tb}.attn2.out.b"] = self._a(sd[f"{tb}.attn2.to_out.0.weight"]), self._f(sd[f"{tb}.attn2.to_out.0.bias"])
-                    for f in ("ff", "fuser.ff"):
-                        w1, b1 = self._pack_geglu(sd[f"{tb}.{f}.net.0.proj.weight"].float(), sd[f"{tb}.{f}.net.0.proj.bias"].float())
-                        W[f"{tb}.{f}.w1"], W[f"{tb}.{f}.b1"] = self._a(w1), self._f(b1)
+                    for f, nrm in (("ff", "norm3"), ("fuser.ff", "fuser.norm2")):
+                        wf, cs, b = self._fold_ln(sd[f"{tb}.{f}.net.0.proj.weight"], sd[f"{tb}.{f}.net.0.proj.bias"],
+                                                  sd[f"{tb}.{nrm}.weight"], sd[f"{tb}.{nrm}.bias"])
+                        w1, s1, b1 = self._pack_geglu(wf, cs, b)
+                        W[f"{tb}.{f}.w1"], W[f"{tb}.{f}.s1"], W[f"{tb}.{f}.b1"] = w1.to(self.dev).contiguous(), self._f(s1), self._f(b1)
                         W[f"{tb}.{f}.w2"], W[f"{tb}.{f}.b2"] = self._a(sd[f"{tb}.{f}.net.2.weight"]), self._f(sd[f"{tb}.{f}.net.2.bias"])
-                    for n in ("norm1", "norm2", "norm3", "fuser.norm1", "fuser.norm2"):
-                        W[f"{tb}.{n}.g"], W[f"{tb}.{n}.b"] = self._f(sd[f"{tb}.{n}.weight"]), self._f(sd[f"{tb}.{n}.bias"])
                     W[f"{tb}.fuser.linear.w"], W[f"{tb}.fuser.linear.b"] = self._a(sd[f"{tb}.fuser.linear.weight"]), self._f(sd[f"{tb}.fuser.linear.bias"])
         W["out.gn.g"], W["out.gn.b"] = self._f(sd["out.0.weight"]), self._f(sd["out.0.bias"])
         W["out.w"] = self._f(sd["out.2.weight"].permute(2, 3, 0, 1).reshape(9, cfg.out_channels, cfg.model_channels))
@@ -228,7 +247,7 @@ class Engine:
     def _sizes(self, Bt: int, N: int, nctx: int) -> Dict[str, int]:
         cfg = self.cfg
         G = N * self.n_streams
-        s = dict(t0=0, sb=0, sc=0, sd=0, up=0, col=0, xs=0, qkv=0, ao=0, ffh=0, ln=0, objp=0, kv=0, blk=0)
+        s = dict(t0=0, sb=0, sc=0, sd=0, up=0, col=0, xs=0, qkv=0, ao=0, ffh=0, xstat=0, blk=0)
         for blk in self.blocks:
             hw = (cfg.image_size // blk.ds) ** 2
             for ly in blk.layers:
@@ -241,11 +260,9 @@ class Engine:
                     s["t0"] = max(s["t0"], Bt * T * C)
                     s["xs"] = max(s["xs"], Bt * T * C)
                     s["ao"] = max(s["ao"], Bt * T * C)
-                    s["qkv"] = max(s["qkv"], Bt * (T + G) * 3 * C)
-                    s["ln"] = max(s["ln"], Bt * (T + G) * C)
+                    s["qkv"] = max(s["qkv"], Bt * T * 3 * C)
                     s["ffh"] = max(s["ffh"], Bt * T * 4 * C)
-                    s["objp"] = max(s["objp"], Bt * G * C)
-                    s["kv"] = max(s["kv"], Bt * nctx * 2 * C)
+                    s["xstat"] = max(s["xstat"], Bt * T * (C // 32) * 2)
                     s["blk"] = max(s["blk"], Bt * T * C)
                 elif ly.kind == "down":
                     s["col"] = max(s["col"], Bt * (hw // 4) * 9 * ly.cin)
@@ -259,7 +276,7 @@ class Engine:
         G = N * S
         P = Plan()
         sz = self._sizes(Bt, N, nctx)
-        B_ = {k: self._buf(v) for k, v in sz.items()}
+        B_ = {k: self._buf(v, torch.float32 if k == "xstat" else None) for k, v in sz.items()}
         B_["blk2"] = self._buf(sz["blk"])
         stats = self._buf(2 * 32 * (Bt + 4 * 148 + 2 * Bt) + Bt + 64, torch.float32)   # GLG_GN_SCRATCH_FLOATS
         Himg = cfg.image_size
@@ -372,47 +389,52 @@ class Engine:
             tb = f"{p}.transformer_blocks.0"
             heads, d = ly.heads, ly.d_head
             gi = st_index[p]
+            NS = C // 32                                   # capacity of the per-row LayerNorm partial-sum slots
             t0 = view("t0", Bt, T, C)
-            xs = view("xs", Bt, T, C)
+            xs = view("xs", Bt, T, C)                      # the residual stream of the block (raw, bf16)
             ao = view("ao", Bt, T, C)
             ffh = view("ffh", Bt, T, 4 * C)
             qkv = view("qkv", Bt, T, 3 * C)
+            xst = view("xstat", Bt * T, NS, 2)             # (sum, sumsq) partials of the CURRENT xs rows
+            EPS = 1e-5
             P.add(f"{p}.gn", lambda: ops.groupnorm(x_in, t0, W[f"{p}.gn.g"], W[f"{p}.gn.b"], stats, 32, 1e-6, False))
-            P.add(f"{p}.proj_in", lambda: ops.gemm(t0, W[f"{p}.proj_in.w"], xs, bias=W[f"{p}.proj_in.b"]))
-            # -- attn1 (attention.py:334)
-            P.add(f"{tb}.norm1", lambda: ops.layernorm(xs, t0, W[f"{tb}.norm1.g"], W[f"{tb}.norm1.b"]))
-            P.add(f"{tb}.attn1.qkv", lambda: ops.gemm(t0, W[f"{tb}.attn1.qkv.w"], qkv))
+            P.add(f"{p}.proj_in", lambda: ops.gemm(t0, W[f"{p}.proj_in.w"], xs, bias=W[f"{p}.proj_in.b"], stats_out=xst))
+            # -- attn1 (attention.py:334); norm1 folded into the QKV GEMM
+            P.add(f"{tb}.attn1.qkv", lambda: ops.gemm(xs, W[f"{tb}.attn1.qkv.w"], qkv, bias=W[f"{tb}.attn1.qkv.b"],
+                                                      ln=(xst, W[f"{tb}.attn1.qkv.s"], EPS)))
             P.add(f"{tb}.attn1.core", lambda: ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], ao, heads, d))
-            P.add(f"{tb}.attn1.out", lambda: ops.gemm(ao, W[f"{tb}.attn1.out.w"], xs, bias=W[f"{tb}.attn1.out.b"], residual=xs))
-            # -- fuser: GatedSelfAttentionDense (attention.py:236-244); skipped when scale == 0
+            P.add(f"{tb}.attn1.out", lambda: ops.gemm(ao, W[f"{tb}.attn1.out.w"], xs, bias=W[f"{tb}.attn1.out.b"], residual=xs, stats_out=xst))
+            # -- fuser: GatedSelfAttentionDense (attention.py:236-244); skipped when scale == 0.
+            #    LN(cat[x, objs']) @ Wqkv is computed as two GEMMs into one per-layer [Bt, T+G, 3C] buffer: the
+            #    visual rows every step, the grounding rows (objs' = linear(objs) is timestep-invariant) once.
             fu = f"{tb}.fuser"
-            objp = self._buf(S * Bt * N * C).view(S, Bt, N, C)        # per layer: static across timesteps
-            ln = view("ln", Bt, T + G, C)
-            qkv2 = view("qkv", Bt, T + G, 3 * C)
+            objp = self._buf(S * Bt * N * C).view(S, Bt * N, C)
+            ostat = self._buf(S * Bt * N * NS * 2, f32).view(S, Bt * N, NS, 2)
+            qkv2 = self._buf(Bt * (T + G) * 3 * C).view(Bt, T + G, 3 * C)
             P.add(f"{fu}.linear", lambda: ops.gemm(objs.view(S * Bt * N, D), W[f"{fu}.linear.w"], objp.view(S * Bt * N, C),
-                                                  bias=W[f"{fu}.linear.b"]), fuser=True, static=True)
-            P.add(f"{fu}.norm1.x", lambda: ops.layernorm(xs, ln[:, :T], W[f"{fu}.norm1.g"], W[f"{fu}.norm1.b"]), fuser=True)
+                                                  bias=W[f"{fu}.linear.b"], stats_out=ostat.view(S * Bt * N, NS, 2)), fuser=True, static=True)
             for si in range(S):
-                P.add(f"{fu}.norm1.objs{si}", lambda si=si: ops.layernorm(objp[si], ln[:, T + si * N: T + (si + 1) * N],
-                                                                         W[f"{fu}.norm1.g"], W[f"{fu}.norm1.b"]), fuser=True)
-            P.add(f"{fu}.attn.qkv", lambda: ops.gemm(ln, W[f"{fu}.attn.qkv.w"], qkv2), fuser=True)
+                P.add(f"{fu}.attn.qkv.objs{si}", lambda si=si: ops.gemm(
+                    objp[si], W[f"{fu}.attn.qkv.w"], qkv2[:, T + si * N: T + (si + 1) * N], bias=W[f"{fu}.attn.qkv.b"],
+                    ln=(ostat[si], W[f"{fu}.attn.qkv.s"], EPS)), fuser=True, static=True)
+            P.add(f"{fu}.attn.qkv", lambda: ops.gemm(xs, W[f"{fu}.attn.qkv.w"], qkv2[:, :T], bias=W[f"{fu}.attn.qkv.b"],
+                                                    ln=(xst, W[f"{fu}.attn.qkv.s"], EPS)), fuser=True)
             P.add(f"{fu}.attn.core", lambda: ops.attention(qkv2[:, :T, :C], qkv2[:, :, C:2 * C], qkv2[:, :, 2 * C:], ao, heads, d), fuser=True)
             P.add(f"{fu}.attn.out", lambda: ops.gemm(ao, W[f"{fu}.attn.out.w"], xs, bias=W[f"{fu}.attn.out.b"],
-                                                    gate=W["gates"][gi, 0:1], residual=xs), fuser=True)
-            P.add(f"{fu}.norm2", lambda: ops.layernorm(xs, t0, W[f"{fu}.norm2.g"], W[f"{fu}.norm2.b"]), fuser=True)
-            P.add(f"{fu}.ff.1", lambda: ops.gemm(t0, W[f"{fu}.ff.w1"], ffh, bias=W[f"{fu}.ff.b1"], geglu=True), fuser=True)
-            P.add(f"{fu}.ff.2", lambda: ops.gemm(ffh, W[f"{fu}.ff.w2"], xs, bias=W[f"{fu}.ff.b2"], gate=W["gates"][gi, 1:2], residual=xs), fuser=True)
-            # -- attn2: cross attention to the text context (attention.py:336)
+                                                    gate=W["gates"][gi, 0:1], residual=xs, stats_out=xst), fuser=True)
+            P.add(f"{fu}.ff.1", lambda: ops.gemm(xs, W[f"{fu}.ff.w1"], ffh, bias=W[f"{fu}.ff.b1"], geglu=True,
+                                                ln=(xst, W[f"{fu}.ff.s1"], EPS)), fuser=True)
+            P.add(f"{fu}.ff.2", lambda: ops.gemm(ffh, W[f"{fu}.ff.w2"], xs, bias=W[f"{fu}.ff.b2"], gate=W["gates"][gi, 1:2],
+                                                residual=xs, stats_out=xst), fuser=True)
+            # -- attn2: cross attention to the text context (attention.py:336); K/V of the context are static
             q = view("ao", Bt, T, C)            # ao is free between attention calls: reuse as Q, write O to t0
             kv = self._buf(Bt * nctx * 2 * C).view(Bt, nctx, 2 * C)  # per layer: static across timesteps
-            P.add(f"{tb}.norm2", lambda: ops.layernorm(xs, t0, W[f"{tb}.norm2.g"], W[f"{tb}.norm2.b"]))
-            P.add(f"{tb}.attn2.q", lambda: ops.gemm(t0, W[f"{tb}.attn2.q.w"], q))
+            P.add(f"{tb}.attn2.q", lambda: ops.gemm(xs, W[f"{tb}.attn2.q.w"], q, bias=W[f"{tb}.attn2.q.b"], ln=(xst, W[f"{tb}.attn2.q.s"], EPS)))
             P.add(f"{tb}.attn2.kv", lambda: ops.gemm(ctx_a, W[f"{tb}.attn2.kv.w"], kv), static=True)
             P.add(f"{tb}.attn2.core", lambda: ops.attention(q, kv[:, :, :C], kv[:, :, C:], t0, heads, d))
-            P.add(f"{tb}.attn2.out", lambda: ops.gemm(t0, W[f"{tb}.attn2.out.w"], xs, bias=W[f"{tb}.attn2.out.b"], residual=xs))
+            P.add(f"{tb}.attn2.out", lambda: ops.gemm(t0, W[f"{tb}.attn2.out.w"], xs, bias=W[f"{tb}.attn2.out.b"], residual=xs, stats_out=xst))
             # -- ff (attention.py:337)
-            P.add(f"{tb}.norm3", lambda: ops.layernorm(xs, t0, W[f"{tb}.norm3.g"], W[f"{tb}.norm3.b"]))
-            P.add(f"{tb}.ff.1", lambda: ops.gemm(t0, W[f"{tb}.ff.w1"], ffh, bias=W[f"{tb}.ff.b1"], geglu=True))
+            P.add(f"{tb}.ff.1", lambda: ops.gemm(xs, W[f"{tb}.ff.w1"], ffh, bias=W[f"{tb}.ff.b1"], geglu=True, ln=(xst, W[f"{tb}.ff.s1"], EPS)))
             P.add(f"{tb}.ff.2", lambda: ops.gemm(ffh, W[f"{tb}.ff.w2"], xs, bias=W[f"{tb}.ff.b2"], residual=xs))
             P.add(f"{p}.proj_out", lambda: ops.gemm(xs, W[f"{p}.proj_out.w"], out, bias=W[f"{p}.proj_out.b"], residual=x_in))
 

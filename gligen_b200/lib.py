@@ -22,6 +22,8 @@ class GlgGemmArgs(C.Structure):
         ("bias", c_void_p), ("rowbias", c_void_p), ("ld_rowbias", c_int64), ("rows_per_batch", c_int),
         ("act", c_int), ("gate", c_void_p), ("residual", c_void_p), ("ldr", c_int64),
         ("geglu", c_int), ("conv_mode", c_int), ("H", c_int), ("Wd", c_int), ("Bn", c_int),
+        ("ln_stats", c_void_p), ("ln_colsum", c_void_p), ("ln_slots", c_int), ("ln_eps", c_float),
+        ("stats_out", c_void_p), ("stats_slots", c_int), ("out_rows_per_batch", c_int), ("out_batch_stride", c_int64),
     ]
 
 
@@ -59,7 +61,7 @@ SIGNATURES = {
                                    c_float, c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 # not part of the public header: test hook
-_DEBUG_SIGNATURES = {"glg_debug_force_bn": (None, [c_int]), "glg_debug_attn_mode": (None, [c_int])}
+_DEBUG_SIGNATURES = {"glg_debug_force_bn": (None, [c_int]), "glg_debug_attn_mode": (None, [c_int]), "glg_debug_attn_poly": (None, [c_int])}
 
 _lib: Optional[C.CDLL] = None
 
@@ -83,7 +85,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.glg_abi_version() != 1:
+    if lib.glg_abi_version() != 2:
         raise GligenLibraryError(f"ABI mismatch: library reports {lib.glg_abi_version()}")
     _lib = lib
     return lib

@@ -63,11 +63,20 @@ class CudaOps:
 
     # -- tensor-core GEMM / conv --------------------------------------------------------------
     def gemm(self, a, w, out, bias=None, rowbias=None, rows_per_batch=1, act=0, gate=None, residual=None,
-             geglu=False, conv=None):
-        """out = epilogue(a @ w.T).  `conv=(B,H,W)` selects the implicit 3x3 convolution (w is [9*N, K])."""
+             geglu=False, conv=None, ln=None, stats_out=None):
+        """out = epilogue(a @ w.T).  `conv=(B,H,W)` selects the implicit 3x3 convolution (w is [9*N, K]).
+        ln=(stats [M,S,2] fp32, colsum [N] fp32, eps): LayerNorm of the A rows folded into the epilogue.
+        stats_out [M,S,2] fp32: per-row partial (sum, sumsq) of the stored output.
+        `out` may be a [B, rows, N] view whose batch stride is not rows*ld (batch-strided rows)."""
         ap, M, K, lda = _rows_view(a)
-        op, Mo, No, ldc = _rows_view(out)
         g = L.GlgGemmArgs()
+        if out.dim() == 3 and out.shape[0] > 1 and out.stride(0) != out.stride(1) * out.shape[1]:
+            assert out.stride(2) == 1
+            op, Mo, No, ldc = out.data_ptr(), out.shape[0] * out.shape[1], out.shape[2], out.stride(1)
+            g.out_rows_per_batch, g.out_batch_stride = out.shape[1], out.stride(0)
+        else:
+            op, Mo, No, ldc = _rows_view(out)
+            g.out_rows_per_batch, g.out_batch_stride = 0, 0
         N = No * 2 if geglu else No
         assert Mo == M, (Mo, M)
         assert w.is_contiguous() and w.shape[1] == K and w.shape[0] == (9 * N if conv else N), (w.shape, N, K)
@@ -94,6 +103,18 @@ class CudaOps:
             g.conv_mode, g.Bn, g.H, g.Wd = 1, conv[0], conv[1], conv[2]
         else:
             g.conv_mode, g.Bn, g.H, g.Wd = 0, 0, 0, 0
+        if ln is not None:
+            st, colsum, eps = ln
+            assert st.dtype == torch.float32 and st.is_contiguous() and st.shape[0] == M and st.shape[2] == 2
+            assert colsum.dtype == torch.float32 and colsum.numel() == N
+            g.ln_stats, g.ln_colsum, g.ln_slots, g.ln_eps = st.data_ptr(), colsum.data_ptr(), st.shape[1], eps
+        else:
+            g.ln_stats, g.ln_colsum, g.ln_slots, g.ln_eps = None, None, 0, 0.0
+        if stats_out is not None:
+            assert stats_out.dtype == torch.float32 and stats_out.is_contiguous() and stats_out.shape[0] == M and stats_out.shape[2] == 2
+            g.stats_out, g.stats_slots = stats_out.data_ptr(), stats_out.shape[1]
+        else:
+            g.stats_out, g.stats_slots = None, 0
         L.check(self.lib.glg_gemm(C.byref(g), self._stream()), "glg_gemm")
         taps = 9 if conv is not None else 1
         self._note("conv3x3" if conv is not None else "gemm", 2.0 * M * N * K * taps,

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GLG_ABI_VERSION 1
+#define GLG_ABI_VERSION 2
 
 #define GLG_ACT_NONE 0
 #define GLG_ACT_SILU 1
@@ -48,6 +48,16 @@ void glg_reset_launch_count(void);
  * geglu=1 (attention.py:42-44): W/bias rows are packed per 256-row tile as [128 x-rows | 128 gate-rows]
  *   and out[M, N/2] = (x + bx) * gelu_erf(g + bg); act/gate/residual are not applied.
  * conv_mode=1: A is an NHWC activation [B, H, W, C=K] (ld = pixel stride); W is [9][N][K]; zero padding 1.
+ *
+ * LayerNorm fold (attention.py:309-311,225-226 nn.LayerNorm feeding a Linear): with W' = W * gamma (per input
+ *   channel, folded into W by the caller), colsum[n] = sum_k W'[n,k] and bias' = bias + W beta,
+ *       LN(x) W^T + bias = rstd_r * (x W'^T - mu_r * colsum) + bias'
+ *   so the GEMM runs on the RAW activations and the normalisation is two per-row scalars in the epilogue:
+ *   ln_stats[M][ln_slots][2] holds partial (sum, sum of squares) of every A row over its K columns (summed in
+ *   slot order); they are produced for free by the GEMM that wrote A when its stats_out is set
+ *   (stats_out[M][stats_slots][2]; one partial per (row, column tile, epilogue-warp half), unused slots zeroed;
+ *   statistics are of the bf16-rounded stored values).  No LayerNorm kernel, no normalised copy in HBM.
+ * out_rows_per_batch > 0: output row r is written at (r / orpb) * out_batch_stride + (r % orpb) * ldc.
  */
 typedef struct GlgGemmArgs {
   const void* A;          /* bf16 */
@@ -68,6 +78,14 @@ typedef struct GlgGemmArgs {
   int32_t geglu;
   int32_t conv_mode;      /* 0 = plain GEMM, 1 = 3x3 stride-1 pad-1 convolution */
   int32_t H, Wd, Bn;      /* conv_mode: spatial dims and batch; M == Bn*H*Wd */
+  const float* ln_stats;  /* LayerNorm fold: [M, ln_slots, 2] fp32 or NULL */
+  const float* ln_colsum; /* [N] fp32 */
+  int32_t ln_slots;
+  float ln_eps;
+  float* stats_out;       /* [M, stats_slots, 2] fp32 or NULL */
+  int32_t stats_slots;
+  int32_t out_rows_per_batch;
+  int64_t out_batch_stride;
 } GlgGemmArgs;
 int glg_gemm(const GlgGemmArgs* args, void* stream);
 

@@ -30,7 +30,7 @@ class RefOps:
 
     # ------------------------------------------------------------------------------------------
     def gemm(self, a, w, out, bias=None, rowbias=None, rows_per_batch=1, act=0, gate=None, residual=None,
-             geglu=False, conv=None):
+             geglu=False, conv=None, ln=None, stats_out=None):
         self.launches += 1
         K = a.shape[-1]
         A = a.reshape(-1, K).float()
@@ -44,6 +44,12 @@ class RefOps:
         else:
             y = A @ Wf.t()
         M = y.shape[0]
+        if ln is not None:       # LayerNorm fold: rstd * (x W'^T - mu * colsum)   (gamma in W', beta in the bias)
+            st, colsum, eps = ln
+            s1, s2 = st[:, :, 0].sum(1), st[:, :, 1].sum(1)
+            mu = s1 / K
+            rstd = torch.rsqrt((s2 / K - mu * mu).clamp_min(0) + eps)
+            y = rstd[:, None] * (y - mu[:, None] * colsum.float()[None])
         if geglu:
             y = y + bias.float()[None]
             n2 = y.shape[1] // 2
@@ -62,7 +68,13 @@ class RefOps:
                 v = v * gate.float()
             if residual is not None:
                 v = v + residual.reshape(M, -1).float()
-        out.copy_(v.view(out.shape).to(out.dtype))
+        stored = v.view(out.shape).to(out.dtype)
+        out.copy_(stored)
+        if stats_out is not None:
+            sv = stored.float().reshape(M, -1)
+            stats_out.zero_()
+            stats_out[:, 0, 0] = sv.sum(1)
+            stats_out[:, 0, 1] = (sv * sv).sum(1)
 
     def attention(self, q, k, v, out, heads, d_head):
         self.launches += 1

@@ -38,9 +38,32 @@ def test_engine_plan_matches_reference(name, gold_file):
     # the fuser steps are really skipped at scale 0 (launch accounting)
     P = next(iter(eng.plans.values()))
     n_fuser = sum(1 for _, fu, st, _ in P.steps if fu)
-    assert n_fuser == 16 * (8 + eng.n_streams)
+    assert n_fuser == 16 * (6 + eng.n_streams)      # linear, qkv(objs) per stream, qkv(x), core, out, ff.1, ff.2
     n_static = sum(1 for _, fu, st, _ in P.steps if st)
-    assert n_static == 4 * eng.n_streams + 1 + 2 * 16          # PositionNet, context cast, attn2.kv + fuser.linear per block
+    assert n_static == 4 * eng.n_streams + 1 + (2 + eng.n_streams) * 16   # PositionNet, context cast; per block: attn2.kv, fuser.linear, fuser qkv of the grounding rows
+
+
+def test_static_steps_follow_their_inputs():
+    """The timestep-invariant part of the plan is cached on the identity of context / grounding tensors: new
+    tensors, or in-place edits of the same tensors, must invalidate it."""
+    from oracle import unet_oracle as UO
+    cfg = NAMED_CONFIGS["tiny"]
+    sd = synthetic_state_dict(cfg, 0)
+    eng = Engine(cfg, RefOps())
+    eng.load_state_dict(sd)
+    inp = synth.make_inputs(cfg, 1, 4, seed=11)
+    ts = torch.tensor([700])
+    ctx = inp["context"].clone()
+    gr = {k: v.clone() for k, v in inp["grounding_input"].items()}
+    for trial in range(3):
+        e = eng.forward(inp["x"], ts, ctx, gr)
+        assert (e - UO.unet_forward(cfg, sd, inp["x"], ts, ctx, gr)).abs().max() < 5e-5, trial
+        if trial == 0:
+            ctx.mul_(0.5)                               # in-place edit, same storage
+        else:
+            gr["boxes"] = (gr["boxes"] * 0.9).contiguous()   # new tensor
+    e2 = eng.forward(inp["x"], ts + 1, ctx, gr)         # same static inputs, new timestep: static part reused
+    assert (e2 - UO.unet_forward(cfg, sd, inp["x"], ts + 1, ctx, gr)).abs().max() < 5e-5
 
 
 def test_first_conv_swap_is_in_place():

@@ -82,6 +82,53 @@ def test_gemm(ops, ref, M, N, K, fl, force_bn):
         assert big[:, :64].abs().max().item() == 0.0, "wrote outside the output slice"
 
 
+@pytest.mark.parametrize("M,N,K,geglu", [(4096, 960, 320, False), (1000, 1920, 640, False), (300, 1280, 1280, False),
+                                         (4096, 2560, 320, True), (520, 1024, 128, True)])
+def test_gemm_layernorm_fold(ops, ref, M, N, K, geglu):
+    """producer GEMM (stats_out) -> consumer GEMM (ln fold) == explicit LayerNorm followed by the GEMM."""
+    import torch.nn.functional as F
+    a0 = rnd(M, 64)
+    w0 = rnd(K, 64, scale=0.3, seed=1)
+    res = rnd(M, K, seed=2) * 2 + 0.7                      # non-zero row means: exercises the mu * colsum cancellation
+    x = torch.zeros(M, K, device="cuda:0", dtype=torch.bfloat16)
+    slots = K // 32
+    st = torch.full((M, slots, 2), 7.0, device="cuda:0")   # poisoned: unused slots must be zeroed by the kernel
+    ops.gemm(a0, w0, x, residual=res, stats_out=st)
+    torch.cuda.synchronize()
+    xf = x.float()
+    assert_close(st[:, :, 0].sum(1), xf.sum(1), rel=1e-5, max_rel=1e-4, what="row sums")
+    assert_close(st[:, :, 1].sum(1), (xf * xf).sum(1), rel=1e-5, max_rel=1e-4, what="row sums of squares")
+    gamma = 1 + 0.2 * rnd(K, seed=3, dtype=torch.float32)
+    beta = 0.2 * rnd(K, seed=4, dtype=torch.float32)
+    w = rnd(N, K, scale=K ** -0.5, seed=5, dtype=torch.float32)
+    bias = rnd(N, seed=6, dtype=torch.float32)
+    wf = (w * gamma[None]).to(torch.bfloat16)
+    colsum = wf.float().sum(1)
+    bfold = bias + w @ beta
+    No = N // 2 if geglu else N
+    out = torch.zeros(M, No, device="cuda:0", dtype=torch.bfloat16)
+    ops.gemm(x, wf, out, bias=bfold, geglu=geglu, ln=(st, colsum, 1e-5))
+    torch.cuda.synchronize()
+    y = F.linear(F.layer_norm(xf, (K,), gamma, beta, 1e-5), w, bias)
+    if geglu:
+        t = y.view(M, N // 256, 2, 128)
+        y = (t[:, :, 0] * F.gelu(t[:, :, 1])).reshape(M, No)
+    assert_close(out, y, what=f"ln-fold gemm {M}x{N}x{K} geglu={geglu}")
+
+
+def test_gemm_batch_strided_output(ops, ref):
+    B, T, G, C = 3, 200, 30, 320
+    a = rnd(B * T, C)
+    w = rnd(3 * C, C, scale=C ** -0.5, seed=1)
+    big = torch.zeros(B, T + G, 3 * C, device="cuda:0", dtype=torch.bfloat16)
+    big_r = torch.zeros_like(big)
+    ops.gemm(a, w, big[:, :T])
+    torch.cuda.synchronize()
+    ref.gemm(a, w, big_r[:, :T])
+    assert_close(big, big_r, what="batch-strided gemm")
+    assert big[:, T:].abs().max().item() == 0
+
+
 CONV_CASES = [
     # B, H, W, Cin, Cout, flags
     (2, 64, 64, 320, 320, dict(rowbias=True)),
