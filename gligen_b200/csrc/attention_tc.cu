@@ -269,7 +269,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
-int g_attn_poly = 4;   // every 4th exp2 on the FMA pipe (test hook: glg_debug_attn_poly)
+int g_attn_poly = 0;   // measured on B200: all-MUFU is fastest (the kernel is not MUFU-bound); 2 / 4 = every 2nd / 4th exp2 on the FMA pipe (glg_debug_attn_poly)
 
 template <int DPAD, int POLY>
 static int launch_attn_tc2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p, int B, cudaStream_t st) {
@@ -289,9 +289,9 @@ static int launch_attn_tc2(const CUtensorMap& tq, const CUtensorMap& tk, const C
 template <int DPAD>
 static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p, int B, cudaStream_t st) {
   switch (g_attn_poly) {
-    case 0: return launch_attn_tc2<DPAD, 0>(tq, tk, tv, p, B, st);
     case 2: return launch_attn_tc2<DPAD, 2>(tq, tk, tv, p, B, st);
-    default: return launch_attn_tc2<DPAD, 4>(tq, tk, tv, p, B, st);
+    case 4: return launch_attn_tc2<DPAD, 4>(tq, tk, tv, p, B, st);
+    default: return launch_attn_tc2<DPAD, 0>(tq, tk, tv, p, B, st);
   }
 }
 

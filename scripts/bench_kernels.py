@@ -64,21 +64,24 @@ for (d, T, G, heads) in ((40, 4096, 30, 8), (80, 1024, 30, 8), (160, 256, 30, 8)
     ops.lib.glg_debug_attn_poly(4)
 
 # ---------------- GEMMs (token GEMMs of the transformer blocks) ----------------
-for (T, C) in ((4096, 320), (1024, 640), (256, 1280), (64, 1280)):
-    M = Bt * T
-    x = rnd(M, C)
-    res = rnd(M, C)
-    bias = torch.randn(C, device=dev)
-    for (nm, N, K, kw) in (("qkv", 3 * C, C, {}), ("proj/out +bias+res", C, C, dict(bias=bias, residual=res)), ("ff2 +bias+res", C, 4 * C, dict(bias=bias, residual=res))):
-        a = rnd(M, K)
-        w = rnd(N, K, scale=K ** -0.5)
-        o = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-        timeit(f"gemm {nm:20s} M={M} N={N} K={K}", lambda: ops.gemm(a, w, o, **kw), flops=2.0 * M * N * K, nbytes=2.0 * (M * K + N * K + M * N))
-    w1 = rnd(8 * C, C, scale=C ** -0.5)
-    b1 = torch.randn(8 * C, device=dev)
-    o1 = torch.empty(M, 4 * C, device=dev, dtype=torch.bfloat16)
-    timeit(f"gemm {'ff1 geglu':20s} M={M} N={8*C} K={C}", lambda: ops.gemm(x, w1, o1, bias=b1, geglu=True), flops=2.0 * M * 8 * C * C, nbytes=2.0 * (M * C + 8 * C * C + M * 4 * C))
+for cta2, cname in ((1, "1cta"), (2, "2cta"), (0, "auto")):
+  ops.lib.glg_debug_gemm_cta2(cta2)
+  for (T, C) in ((4096, 320), (1024, 640), (256, 1280), (64, 1280)):
+      M = Bt * T
+      x = rnd(M, C)
+      res = rnd(M, C)
+      bias = torch.randn(C, device=dev)
+      for (nm, N, K, kw) in (("qkv", 3 * C, C, {}), ("proj/out +bias+res", C, C, dict(bias=bias, residual=res)), ("ff2 +bias+res", C, 4 * C, dict(bias=bias, residual=res))):
+          a = rnd(M, K)
+          w = rnd(N, K, scale=K ** -0.5)
+          o = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+          timeit(f"gemm[{cname}] {nm:20s} M={M} N={N} K={K}", lambda: ops.gemm(a, w, o, **kw), flops=2.0 * M * N * K, nbytes=2.0 * (M * K + N * K + M * N))
+      w1 = rnd(8 * C, C, scale=C ** -0.5)
+      b1 = torch.randn(8 * C, device=dev)
+      o1 = torch.empty(M, 4 * C, device=dev, dtype=torch.bfloat16)
+      timeit(f"gemm[{cname}] {'ff1 geglu':20s} M={M} N={8*C} K={C}", lambda: ops.gemm(x, w1, o1, bias=b1, geglu=True), flops=2.0 * M * 8 * C * C, nbytes=2.0 * (M * C + 8 * C * C + M * 4 * C))
 
+ops.lib.glg_debug_gemm_cta2(0)
 # ---------------- conv3x3 ----------------
 for (H, Cin, Cout) in ((64, 320, 320), (64, 960, 320), (64, 640, 320), (64, 640, 640), (32, 640, 640), (32, 1920, 640), (32, 1280, 1280), (16, 1280, 1280), (16, 2560, 1280), (8, 1280, 1280), (8, 2560, 1280)):
     a = rnd(Bt, H * H, Cin)
@@ -86,8 +89,11 @@ for (H, Cin, Cout) in ((64, 320, 320), (64, 960, 320), (64, 640, 320), (64, 640,
     o = torch.empty(Bt, H * H, Cout, device=dev, dtype=torch.bfloat16)
     bias = torch.randn(Cout, device=dev)
     res = rnd(Bt, H * H, Cout)
-    timeit(f"conv3x3 {H}x{H} {Cin}->{Cout}", lambda: ops.gemm(a, w, o, bias=bias, residual=res, conv=(Bt, H, H)), flops=18.0 * Bt * H * H * Cin * Cout,
-           nbytes=2.0 * (Bt * H * H * (Cin + 2 * Cout) + 9 * Cin * Cout))
+    for cta2, cname in ((1, "1cta"), (2, "2cta")):
+        ops.lib.glg_debug_gemm_cta2(cta2)
+        timeit(f"conv3x3[{cname}] {H}x{H} {Cin}->{Cout}", lambda: ops.gemm(a, w, o, bias=bias, residual=res, conv=(Bt, H, H)), flops=18.0 * Bt * H * H * Cin * Cout,
+               nbytes=2.0 * (Bt * H * H * (Cin + 2 * Cout) + 9 * Cin * Cout))
+    ops.lib.glg_debug_gemm_cta2(0)
 
 # ---------------- norms ----------------
 stats = torch.zeros(2 * 32 * (Bt + 4 * 148 + 2 * Bt) + Bt + 64, device=dev)

@@ -46,11 +46,17 @@ GEMM_CASES = [
 
 @pytest.mark.parametrize("M,N,K,fl", GEMM_CASES)
 @pytest.mark.parametrize("force_bn", [0, 64, 128, 160, 256])
-def test_gemm(ops, ref, M, N, K, fl, force_bn):
+@pytest.mark.parametrize("cta2", [0, 1, 2])
+def test_gemm(ops, ref, M, N, K, fl, force_bn, cta2):
+    """cta2: 0 = tile heuristic, 1 = single-CTA kernel (cta_group::1), 2 = paired kernel (cluster of 2, cta_group::2)."""
     if force_bn and (N % force_bn or fl.get("geglu")):
         pytest.skip("BN does not divide N")
     if force_bn and M > 5000:
         pytest.skip("large case only with the heuristic tile")
+    if cta2 == 2 and (force_bn == 64 or M <= 128):
+        pytest.skip("pairs need BN >= 128 and M > 128")
+    if cta2 == 0 and force_bn:
+        pytest.skip("forced tiles are covered by the explicit modes")
     a = rnd(M, K)
     w = rnd(N, K, scale=K ** -0.5, seed=1)
     geglu = fl.get("geglu", False)
@@ -71,20 +77,31 @@ def test_gemm(ops, ref, M, N, K, fl, force_bn):
     kw = dict(bias=bias, rowbias=rowbias, rows_per_batch=max(rows_per_batch, 1), act=1 if fl.get("act") else 0,
               gate=gate, residual=residual, geglu=geglu)
     ops.lib.glg_debug_force_bn(force_bn)
+    ops.lib.glg_debug_gemm_cta2(cta2)
     try:
         ops.gemm(a, w, out, **kw)
         torch.cuda.synchronize()
     finally:
         ops.lib.glg_debug_force_bn(0)
+        ops.lib.glg_debug_gemm_cta2(0)
     ref.gemm(a, w, out_r, **kw)
-    assert_close(out, out_r, what=f"gemm {M}x{N}x{K} {fl} bn={force_bn}")
+    assert_close(out, out_r, what=f"gemm {M}x{N}x{K} {fl} bn={force_bn} cta2={cta2}")
     if fl.get("strided"):
         assert big[:, :64].abs().max().item() == 0.0, "wrote outside the output slice"
 
 
 @pytest.mark.parametrize("M,N,K,geglu", [(4096, 960, 320, False), (1000, 1920, 640, False), (300, 1280, 1280, False),
                                          (4096, 2560, 320, True), (520, 1024, 128, True)])
-def test_gemm_layernorm_fold(ops, ref, M, N, K, geglu):
+@pytest.mark.parametrize("cta2", [1, 2])
+def test_gemm_layernorm_fold(ops, ref, M, N, K, geglu, cta2):
+    ops.lib.glg_debug_gemm_cta2(cta2)
+    try:
+        _ln_fold_case(ops, ref, M, N, K, geglu)
+    finally:
+        ops.lib.glg_debug_gemm_cta2(0)
+
+
+def _ln_fold_case(ops, ref, M, N, K, geglu):
     """producer GEMM (stats_out) -> consumer GEMM (ln fold) == explicit LayerNorm followed by the GEMM."""
     import torch.nn.functional as F
     a0 = rnd(M, 64)
@@ -96,8 +113,9 @@ def test_gemm_layernorm_fold(ops, ref, M, N, K, geglu):
     ops.gemm(a0, w0, x, residual=res, stats_out=st)
     torch.cuda.synchronize()
     xf = x.float()
-    assert_close(st[:, :, 0].sum(1), xf.sum(1), rel=1e-5, max_rel=1e-4, what="row sums")
-    assert_close(st[:, :, 1].sum(1), (xf * xf).sum(1), rel=1e-5, max_rel=1e-4, what="row sums of squares")
+    # statistics are taken before the bf16 rounding of the stored values (zero-mean noise, ~2^-9 relative per element)
+    assert_close(st[:, :, 0].sum(1), xf.sum(1), rel=1e-3, max_rel=5e-3, what="row sums")
+    assert_close(st[:, :, 1].sum(1), (xf * xf).sum(1), rel=1e-3, max_rel=5e-3, what="row sums of squares")
     gamma = 1 + 0.2 * rnd(K, seed=3, dtype=torch.float32)
     beta = 0.2 * rnd(K, seed=4, dtype=torch.float32)
     w = rnd(N, K, scale=K ** -0.5, seed=5, dtype=torch.float32)
@@ -144,7 +162,18 @@ CONV_CASES = [
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,fl", CONV_CASES)
-def test_conv3x3(ops, ref, B, H, W, Cin, Cout, fl):
+@pytest.mark.parametrize("cta2", [1, 2])
+def test_conv3x3(ops, ref, B, H, W, Cin, Cout, fl, cta2):
+    if cta2 == 2 and (B * H * W <= 128 or Cout % 128):
+        pytest.skip("pairs need M > 128 and Cout % 128 == 0")
+    ops.lib.glg_debug_gemm_cta2(cta2)
+    try:
+        _conv_case(ops, ref, B, H, W, Cin, Cout, fl)
+    finally:
+        ops.lib.glg_debug_gemm_cta2(0)
+
+
+def _conv_case(ops, ref, B, H, W, Cin, Cout, fl):
     if fl.get("strided"):
         big = rnd(B, H * W, Cin + 192)
         a = big[:, :, 64:64 + Cin]
