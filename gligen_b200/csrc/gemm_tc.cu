@@ -48,6 +48,7 @@ struct GemmKParams {
   float* stats_out; int stats_slots;
   // batch-strided output rows: address = (row / orpb) * obs + (row % orpb) * ldc   (orpb == 0: uniform rows)
   int orpb; long long obs;
+  int wide;                       // 1: rows of out / residual are 32-byte aligned -> 256-bit global accesses
 };
 
 template <int BN, bool CTA2> struct GemmCfg {
@@ -116,16 +117,45 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
-__device__ __forceinline__ void epi_store_bf16(bf16* dst, const float (&v)[32]) {
+// 256-bit global accesses (sm_100: STG/LDG.256): a thread's 64-byte bf16 row chunk leaves as two full 32-byte
+// sectors instead of four half-sector writes (which doubled the L1->L2 crossbar write traffic).
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const void* p, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(p));
+}
+__device__ __forceinline__ void epi_store_packed(bf16* dst, const uint32_t (&pk)[16], bool wide) {
+  if (wide) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      uint32_t r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = pk[8 * i + j];
+      st_global_256(dst + 16 * i, r);
+    }
+    return;
+  }
   uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 u;
-    u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-    u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-    u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-    u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-    d4[i] = u;
+  for (int i = 0; i < 4; ++i) d4[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+}
+__device__ __forceinline__ void epi_store_bf16(bf16* dst, const float (&v)[32], bool wide) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+  epi_store_packed(dst, pk, wide);
+}
+__device__ __forceinline__ void load_res_chunk(const bf16* src, uint4 (&r)[4], bool wide) {
+  if (wide) {
+    ld_global_256(src, r[0], r[1]);
+    ld_global_256(src + 16, r[2], r[3]);
+  } else {
+    const uint4* r4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = __ldg(r4 + i);
   }
 }
 
@@ -136,7 +166,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
                                               float ln_mu, float ln_rstd, uint4 (&res_pre)[4]) {
   const bool row_ok = row < p.M;
   const size_t out_off = p.orpb ? (size_t)(row / p.orpb) * p.obs + (size_t)(row % p.orpb) * p.ldc : (size_t)row * p.ldc;
-  float st_sum = 0.f, st_sq = 0.f;
   if constexpr (GEGLU) {
     constexpr int HALF = BN / 2;
     constexpr int NCH = HALF / 32;
@@ -175,7 +204,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
         v[j + 2] = (__uint_as_float(rx[j + 2]) + tx.z) * gelu_erf_f(__uint_as_float(rg[j + 2]) + tg.z);
         v[j + 3] = (__uint_as_float(rx[j + 3]) + tx.w) * gelu_erf_f(__uint_as_float(rg[j + 3]) + tg.w);
       }
-      if (row_ok) epi_store_bf16(reinterpret_cast<bf16*>(p.out) + out_off + (size_t)n_blk * HALF + c * 32, v);
+      if (row_ok) epi_store_bf16(reinterpret_cast<bf16*>(p.out) + out_off + (size_t)n_blk * HALF + c * 32, v, p.wide != 0);
     }
   } else {
     const float* rb = (p.rowbias && row_ok) ? p.rowbias + (size_t)(row / p.rows_per_batch) * p.ld_rowbias : nullptr;
@@ -190,11 +219,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
       uint4 res_cur[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) res_cur[i] = res_pre[i];
-      if (has_res && c + 1 < c_end) {           // next chunk's residual: in flight while this chunk is processed
-        const uint4* r4 = reinterpret_cast<const uint4*>(res_row + (c + 1) * 32);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) res_pre[i] = __ldg(r4 + i);
-      }
+      if (has_res && c + 1 < c_end)             // next chunk's residual: in flight while this chunk is processed
+        load_res_chunk(res_row + (c + 1) * 32, res_pre, p.wide != 0);
       tmem_ld_wait();
       const int n0 = n_blk * BN + c * 32;
       float v[32];
@@ -246,22 +272,26 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
 #pragma unroll
           for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         } else {
-          if (p.stats_out) {
-            // fp32 statistics of the values before bf16 rounding: the rounding noise is zero-mean and its effect
-            // on the consumer's mean/variance (~1e-4 relative) is far below the bf16 resolution of its output
+          uint32_t pk[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { st_sum += v[j]; st_sq = fmaf(v[j], v[j], st_sq); }
+          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          if (p.stats_out) {
+            // statistics of the values AS STORED (bf16-rounded): exactly what the consumer GEMM reads.  One partial
+            // per 32-column chunk, slot = global chunk index: independent of the tile shape, so the consumer's
+            // fixed-order sum is bit-identical whatever kernel variant produced the rows.
+            float st_sum = 0.f, st_sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 f = unpack_bf16x2(pk[j]);
+              st_sum += f.x + f.y;
+              st_sq = fmaf(f.x, f.x, fmaf(f.y, f.y, st_sq));
+            }
+            reinterpret_cast<float2*>(p.stats_out)[(size_t)row * p.stats_slots + (n0 >> 5)] = make_float2(st_sum, st_sq);
           }
-          epi_store_bf16(reinterpret_cast<bf16*>(p.out) + out_off + n0, v);
+          epi_store_packed(reinterpret_cast<bf16*>(p.out) + out_off + n0, pk, p.wide != 0);
         }
       }
     }
-  }
-  if (p.stats_out && row_ok) {
-    float2* so = reinterpret_cast<float2*>(p.stats_out) + (size_t)row * p.stats_slots;
-    so[n_blk * 2 + half] = make_float2(st_sum, st_sq);
-    if (n_blk == 0 && half == 0)
-      for (int i = 2 * p.tiles_n; i < p.stats_slots; ++i) so[i] = make_float2(0.f, 0.f);
   }
 }
 
@@ -318,7 +348,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         y0 = (row0 - b0 * p.HW) / p.Wd;
       }
       const int brow0 = n_blk * BN + (int)rank * Cfg::BROWS;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      // K steps are visited in a per-tile rotated order: tiles running at the same time would otherwise request
+      // the very same weight (and activation) lines from L2 in lockstep; the rotation spreads them over slices.
+      // (fp32 accumulation order depends only on the tile index -> results stay reproducible.)
+      int kb = (int)(((unsigned)tile * 3u) % (unsigned)p.num_kb);
+      for (int it = 0; it < p.num_kb; ++it, kb = (kb + 1 == p.num_kb) ? 0 : kb + 1) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         // the leader's barrier collects the bytes of both CTAs
         if (!CTA2) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
@@ -398,11 +432,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (!GEGLU && p.residual && row < p.M) {
         constexpr int NCH = BN / 32;
         const int c_begin = half ? (NCH + 1) / 2 : 0, c_end = half ? NCH : (NCH + 1) / 2;
-        if (c_begin < c_end) {
-          const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + (size_t)n_blk * BN + c_begin * 32);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) res_pre[i] = __ldg(r4 + i);
-        }
+        if (c_begin < c_end)
+          load_res_chunk(p.residual + (size_t)row * p.ldr + (size_t)n_blk * BN + c_begin * 32, res_pre, p.wide != 0);
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -541,8 +572,8 @@ extern "C" int glg_gemm(const GlgGemmArgs* a, void* stream) {
     p.ln_stats = a->ln_stats; p.ln_slots = a->ln_slots; p.ln_colsum = a->ln_colsum; p.ln_eps = a->ln_eps; p.inv_k = 1.0f / (float)a->K;
   }
   if (a->stats_out) {
-    if (a->geglu || a->out_fp32 || 2 * p.tiles_n > a->stats_slots || ((uintptr_t)a->stats_out & 7))
-      return set_error("glg_gemm: stats_out needs a bf16 non-GEGLU output and stats_slots >= 2 * ceil(N / tile)");
+    if (a->geglu || a->out_fp32 || a->stats_slots * 32 != a->N || ((uintptr_t)a->stats_out & 7))
+      return set_error("glg_gemm: stats_out needs a bf16 non-GEGLU output and stats_slots == N / 32");
     p.stats_out = a->stats_out; p.stats_slots = a->stats_slots;
   }
   if (a->out_rows_per_batch > 0) {
@@ -550,6 +581,8 @@ extern "C" int glg_gemm(const GlgGemmArgs* a, void* stream) {
     p.orpb = a->out_rows_per_batch; p.obs = a->out_batch_stride;
   }
   if (a->bias && ((uintptr_t)a->bias & 15)) return set_error("glg_gemm: bias must be 16-byte aligned");
+  p.wide = !a->out_fp32 && !((uintptr_t)a->out & 31) && !(a->ldc % 16) && !(a->out_batch_stride % 16) &&
+           (!a->residual || (!((uintptr_t)a->residual & 31) && !(a->ldr % 16)));
 
   const uint32_t brows = (uint32_t)(cta2 ? bn / 2 : bn);
   CUtensorMap ta, tb;

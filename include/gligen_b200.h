@@ -55,8 +55,8 @@ void glg_reset_launch_count(void);
  *   so the GEMM runs on the RAW activations and the normalisation is two per-row scalars in the epilogue:
  *   ln_stats[M][ln_slots][2] holds partial (sum, sum of squares) of every A row over its K columns (summed in
  *   slot order); they are produced for free by the GEMM that wrote A when its stats_out is set
- *   (stats_out[M][stats_slots][2]; one partial per (row, column tile, epilogue-warp half), unused slots zeroed;
- *   statistics are of the bf16-rounded stored values).  No LayerNorm kernel, no normalised copy in HBM.
+ *   (stats_out[M][N/32][2]: one partial per (row, 32-column chunk) of the bf16-rounded stored values - a layout
+ *   independent of the tile shape, so results are bit-reproducible).  No LayerNorm kernel, no normalised copy in HBM.
  * out_rows_per_batch > 0: output row r is written at (r / orpb) * out_batch_stride + (r % orpb) * ldc.
  */
 typedef struct GlgGemmArgs {

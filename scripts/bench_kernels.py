@@ -82,6 +82,12 @@ for cta2, cname in ((1, "1cta"), (2, "2cta"), (0, "auto")):
       timeit(f"gemm[{cname}] {'ff1 geglu':20s} M={M} N={8*C} K={C}", lambda: ops.gemm(x, w1, o1, bias=b1, geglu=True), flops=2.0 * M * 8 * C * C, nbytes=2.0 * (M * C + 8 * C * C + M * 4 * C))
 
 ops.lib.glg_debug_gemm_cta2(0)
+for cta2, cname in ((1, "1cta"), (2, "2cta")):
+    ops.lib.glg_debug_gemm_cta2(cta2)
+    for (M, N, K) in ((4096, 4096, 4096), (8192, 8192, 8192)):
+        a = rnd(M, K); w = rnd(N, K, scale=K ** -0.5); o = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        timeit(f"gemm[{cname}] square M={M} N={N} K={K}", lambda: ops.gemm(a, w, o), flops=2.0 * M * N * K, nbytes=2.0 * (M * K + N * K + M * N), iters=5)
+ops.lib.glg_debug_gemm_cta2(0)
 # ---------------- conv3x3 ----------------
 for (H, Cin, Cout) in ((64, 320, 320), (64, 960, 320), (64, 640, 320), (64, 640, 640), (32, 640, 640), (32, 1920, 640), (32, 1280, 1280), (16, 1280, 1280), (16, 2560, 1280), (8, 1280, 1280), (8, 2560, 1280)):
     a = rnd(Bt, H * H, Cin)

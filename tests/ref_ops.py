@@ -71,10 +71,9 @@ class RefOps:
         stored = v.view(out.shape).to(out.dtype)
         out.copy_(stored)
         if stats_out is not None:
-            sv = stored.float().reshape(M, -1)
-            stats_out.zero_()
-            stats_out[:, 0, 0] = sv.sum(1)
-            stats_out[:, 0, 1] = (sv * sv).sum(1)
+            sv = stored.float().reshape(M, -1, 32)               # one partial per 32-column chunk
+            stats_out[:, :, 0] = sv.sum(2)
+            stats_out[:, :, 1] = (sv * sv).sum(2)
 
     def attention(self, q, k, v, out, heads, d_head):
         self.launches += 1
