@@ -78,6 +78,8 @@ __device__ __forceinline__ void load_tile(uint32_t smem_tile, const bf16* g, lon
 
 template <int DPAD>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnKParams p) {
+  pdl_trigger();
+  pdl_wait();
   using Cfg = AttnCfg<DPAD>;
   constexpr int LDS = Cfg::LDS;
   constexpr int KSTEPS = DPAD / 16;       // k-steps of QK^T
@@ -242,7 +244,7 @@ static int launch_attn(const AttnKParams& p, int B, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid((p.Lq + 63) / 64, p.heads, B);
-  kern<<<grid, 128, Cfg::SMEM_BYTES, st>>>(p);
+  launch_k(kern, dim3(grid), dim3(128), Cfg::SMEM_BYTES, st, 1, p);
   count_launch();
   return check_launch("attention launch");
 }

@@ -82,6 +82,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t tmem_slot = bar_base + 8u * (8 + 2 * STAGES);
   const uint32_t xch = bar_base + 256;          // float [2][2][128]
 
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BM;
   const int h = blockIdx.y, b = blockIdx.z;
@@ -105,6 +106,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -281,7 +283,7 @@ static int launch_attn_tc2(const CUtensorMap& tq, const CUtensorMap& tk, const C
     attr_set = true;
   }
   dim3 grid((p.Lq + atc::BM - 1) / atc::BM, p.heads, B);
-  kern<<<grid, 320, atc::SMEM_BYTES, st>>>(tq, tk, tv, p);
+  launch_k(kern, grid, dim3(320), atc::SMEM_BYTES, st, 1, tq, tk, tv, p);
   count_launch();
   return check_launch("attention_tc launch");
 }

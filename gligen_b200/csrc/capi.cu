@@ -1,5 +1,6 @@
 // C-ABI plumbing: error strings, launch counter.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <atomic>
 #include <string>
 
@@ -19,6 +20,14 @@ int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(std::string(what) + ": " + cudaGetErrorString(e));
   return 0;
+}
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GLG_PDL");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
 }
 }  // namespace glg
 

@@ -14,6 +14,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel
+// in the stream may be scheduled (and run its prologue: barrier init, TMEM alloc, descriptor prefetch) while this
+// one drains; pdl_wait() blocks until the previous grid has completed and its memory is visible, so it must precede
+// the first access to global data.  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

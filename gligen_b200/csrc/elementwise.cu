@@ -21,6 +21,8 @@ static inline unsigned blocks_for(long long n, int threads) {
 __global__ void conv_in_kernel(const float* __restrict__ x, int C0, const float* __restrict__ extra, int C1,
                                const float* __restrict__ w, const float* __restrict__ bias, bf16* __restrict__ out,
                                long long ldo, int B, int H, int W, int Cout) {
+  pdl_trigger();
+  pdl_wait();
   const int cov = Cout >> 3;
   const long long total = (long long)B * H * W * cov;
   const int Cin = C0 + C1;
@@ -56,6 +58,8 @@ __global__ void conv_in_kernel(const float* __restrict__ x, int C0, const float*
 template <int COUT>
 __global__ void conv_out_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ w,
                                 const float* __restrict__ bias, float* __restrict__ out, int B, int H, int W, int Cin) {
+  pdl_trigger();
+  pdl_wait();
   const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (pix >= (long long)B * H * W) return;
   const int lane = threadIdx.x & 31;
@@ -95,6 +99,8 @@ __global__ void conv_out_kernel(const bf16* __restrict__ x, long long ldx, const
 
 __global__ void upsample2x_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
                                   int B, int H, int W, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int vec = C >> 3;
   const int Ho = 2 * H, Wo = 2 * W;
   const long long total = (long long)B * Ho * Wo * vec;
@@ -109,6 +115,8 @@ __global__ void upsample2x_kernel(const bf16* __restrict__ x, long long ldx, bf1
 }
 
 __global__ void im2col_s2_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, int B, int H, int W, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int vec = C >> 3;
   const int Ho = H / 2, Wo = W / 2;
   const long long total = (long long)B * Ho * Wo * 9 * vec;
@@ -128,6 +136,8 @@ __global__ void im2col_s2_kernel(const bf16* __restrict__ x, long long ldx, bf16
 }
 
 __global__ void copy_rows_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy, long long rows, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int vec = C >> 3;
   const long long total = rows * vec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -137,6 +147,8 @@ __global__ void copy_rows_kernel(const bf16* __restrict__ x, long long ldx, bf16
 }
 
 __global__ void timestep_embedding_kernel(const long long* __restrict__ t, bf16* __restrict__ out, int B, int dim) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * dim) return;
   const int b = i / dim, j = i % dim;
@@ -151,6 +163,8 @@ __global__ void position_features_kernel(const float* __restrict__ feat, long lo
                                          const float* __restrict__ null_feat, const float* __restrict__ coords,
                                          const float* __restrict__ pos_mask, const float* __restrict__ null_pos,
                                          bf16* __restrict__ out, long long ldo, int B, int N, int F, int ncoord, int freqs) {
+  pdl_trigger();
+  pdl_wait();
   const int P = freqs * 2 * ncoord;
   const long long total = (long long)B * N * ldo;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -177,6 +191,8 @@ __global__ void position_features_kernel(const float* __restrict__ feat, long lo
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = __float2bfloat16(x[i]);
 }
@@ -186,6 +202,8 @@ __global__ void sampler_update_kernel(const float* __restrict__ x, const float* 
                                       float c0, float c1, float c2, float c3, float sqrt_at, float sqrt_1m_at,
                                       float sqrt_aprev, float sqrt_1m_aprev,
                                       float* __restrict__ e_out, float* __restrict__ x_prev, long long n) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float e = ec[i];
     if (eu) { const float u = eu[i]; e = u + g * (e - u); }
@@ -209,7 +227,7 @@ extern "C" int glg_conv_in(const float* x, int32_t C0, const float* extra, int32
   if (Cout % 8 || ldo % 8) return set_error("glg_conv_in: Cout and ldo must be multiples of 8");
   if (C1 > 0 && !extra) return set_error("glg_conv_in: extra channels requested but pointer is null");
   const long long total = (long long)B * H * Wd * (Cout / 8);
-  conv_in_kernel<<<blocks_for(total, 256), 256, 0, ST>>>(x, C0, extra, C1, w, bias, (bf16*)out, ldo, B, H, Wd, Cout);
+  launch_k(conv_in_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, ST, 1, x, C0, extra, C1, w, bias, (bf16*)out, ldo, B, H, Wd, Cout);
   count_launch();
   return check_launch("conv_in launch");
 }
@@ -219,8 +237,8 @@ extern "C" int glg_conv_out(const void* x, int64_t ldx, const float* w, const fl
   if (Cin % 8 || ldx % 8) return set_error("glg_conv_out: Cin and ldx must be multiples of 8");
   const long long pix = (long long)B * H * Wd;
   const unsigned grid = blocks_for(pix, 8);
-  if (Cout == 4) conv_out_kernel<4><<<grid, 256, 0, ST>>>((const bf16*)x, ldx, w, bias, out, B, H, Wd, Cin);
-  else if (Cout == 8) conv_out_kernel<8><<<grid, 256, 0, ST>>>((const bf16*)x, ldx, w, bias, out, B, H, Wd, Cin);
+  if (Cout == 4) launch_k(conv_out_kernel<4>, dim3(grid), dim3(256), 0, ST, 1, (const bf16*)x, ldx, w, bias, out, B, H, Wd, Cin);
+  else if (Cout == 8) launch_k(conv_out_kernel<8>, dim3(grid), dim3(256), 0, ST, 1, (const bf16*)x, ldx, w, bias, out, B, H, Wd, Cin);
   else return set_error("glg_conv_out: Cout must be 4 or 8");
   count_launch();
   return check_launch("conv_out launch");
@@ -229,7 +247,7 @@ extern "C" int glg_conv_out(const void* x, int64_t ldx, const float* w, const fl
 extern "C" int glg_upsample2x(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t B, int32_t H, int32_t Wd, int32_t C, void* stream) {
   if (C % 8 || ldx % 8 || ldy % 8) return set_error("glg_upsample2x: C and leading dims must be multiples of 8");
   const long long total = (long long)B * 4 * H * Wd * (C / 8);
-  upsample2x_kernel<<<blocks_for(total, 256), 256, 0, ST>>>((const bf16*)x, ldx, (bf16*)y, ldy, B, H, Wd, C);
+  launch_k(upsample2x_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, ST, 1, (const bf16*)x, ldx, (bf16*)y, ldy, B, H, Wd, C);
   count_launch();
   return check_launch("upsample2x launch");
 }
@@ -237,21 +255,21 @@ extern "C" int glg_upsample2x(const void* x, int64_t ldx, void* y, int64_t ldy, 
 extern "C" int glg_im2col_s2(const void* x, int64_t ldx, void* y, int32_t B, int32_t H, int32_t Wd, int32_t C, void* stream) {
   if (C % 8 || ldx % 8 || (H & 1) || (Wd & 1)) return set_error("glg_im2col_s2: C % 8, even H/W required");
   const long long total = (long long)B * (H / 2) * (Wd / 2) * 9 * (C / 8);
-  im2col_s2_kernel<<<blocks_for(total, 256), 256, 0, ST>>>((const bf16*)x, ldx, (bf16*)y, B, H, Wd, C);
+  launch_k(im2col_s2_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, ST, 1, (const bf16*)x, ldx, (bf16*)y, B, H, Wd, C);
   count_launch();
   return check_launch("im2col_s2 launch");
 }
 
 extern "C" int glg_copy_rows(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int32_t C, void* stream) {
   if (C % 8 || ldx % 8 || ldy % 8) return set_error("glg_copy_rows: C and leading dims must be multiples of 8");
-  copy_rows_kernel<<<blocks_for(rows * (C / 8), 256), 256, 0, ST>>>((const bf16*)x, ldx, (bf16*)y, ldy, rows, C);
+  launch_k(copy_rows_kernel, dim3(blocks_for(rows * (C / 8), 256)), dim3(256), 0, ST, 1, (const bf16*)x, ldx, (bf16*)y, ldy, rows, C);
   count_launch();
   return check_launch("copy_rows launch");
 }
 
 extern "C" int glg_timestep_embedding(const int64_t* t, void* out, int32_t B, int32_t dim, void* stream) {
   if (dim % 2) return set_error("glg_timestep_embedding: dim must be even");
-  timestep_embedding_kernel<<<blocks_for((long long)B * dim, 256), 256, 0, ST>>>((const long long*)t, (bf16*)out, B, dim);
+  launch_k(timestep_embedding_kernel, dim3(blocks_for((long long)B * dim, 256)), dim3(256), 0, ST, 1, (const long long*)t, (bf16*)out, B, dim);
   count_launch();
   return check_launch("timestep_embedding launch");
 }
@@ -260,14 +278,14 @@ extern "C" int glg_position_features(const float* feat, int64_t feat_batch_strid
                                      const float* coords, const float* pos_mask, const float* null_pos, void* out, int64_t ldo,
                                      int32_t B, int32_t N, int32_t F, int32_t ncoord, int32_t freqs, void* stream) {
   if (ldo < F + freqs * 2 * ncoord) return set_error("glg_position_features: ldo too small");
-  position_features_kernel<<<blocks_for((long long)B * N * ldo, 256), 256, 0, ST>>>(feat, feat_batch_stride, feat_mask, null_feat, coords,
+  launch_k(position_features_kernel, dim3(blocks_for((long long)B * N * ldo, 256)), dim3(256), 0, ST, 1, feat, feat_batch_stride, feat_mask, null_feat, coords,
                                                                                     pos_mask, null_pos, (bf16*)out, ldo, B, N, F, ncoord, freqs);
   count_launch();
   return check_launch("position_features launch");
 }
 
 extern "C" int glg_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream) {
-  cast_f32_bf16_kernel<<<blocks_for(n, 256) > 4096 ? 4096 : blocks_for(n, 256), 256, 0, ST>>>(x, (bf16*)y, n);
+  launch_k(cast_f32_bf16_kernel, dim3(blocks_for(n, 256) > 4096 ? 4096 : blocks_for(n, 256)), dim3(256), 0, ST, 1, x, (bf16*)y, n);
   count_launch();
   return check_launch("cast launch");
 }
@@ -276,7 +294,7 @@ extern "C" int glg_sampler_update(const float* x, const float* e_cond, const flo
                                   const float* old1, const float* old2, const float* old3,
                                   float c0, float c1, float c2, float c3, float a_t, float a_prev,
                                   float* e_out, float* x_prev, int64_t n, void* stream) {
-  sampler_update_kernel<<<blocks_for(n, 256), 256, 0, ST>>>(x, e_cond, e_uncond, guidance, old1, old2, old3, c0, c1, c2, c3,
+  launch_k(sampler_update_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, ST, 1, x, e_cond, e_uncond, guidance, old1, old2, old3, c0, c1, c2, c3,
                                                             sqrtf(a_t), sqrtf(1.f - a_t), sqrtf(a_prev), sqrtf(1.f - a_prev), e_out, x_prev, n);
   count_launch();
   return check_launch("sampler_update launch");

@@ -58,8 +58,12 @@ template <int BN, bool CTA2> struct GemmCfg {
   static constexpr int B_BYTES = BROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (196 * 1024) / STAGE_BYTES > 8 ? 8 : (196 * 1024) / STAGE_BYTES;
-  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  // accumulator stages in TMEM: short-K tiles are bound by the MMA <-> epilogue hand-off latency, so use as many
+  // stages as the 512 columns allow (BN=256: 2, 160: 3, <=128: 4)
+  static constexpr int ACC = (512 / BN) > 4 ? 4 : (512 / BN);
+  static constexpr int TMEM_COLS = (ACC * BN <= 128) ? 128 : (ACC * BN <= 256) ? 256 : 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(8 * (2 * STAGES + 2 * ACC) + 8 <= 256, "barrier area");
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment of the next A stage");
 };
 
@@ -212,16 +216,20 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
     const int c_begin = half ? (NCH + 1) / 2 : 0, c_end = half ? NCH : (NCH + 1) / 2;
     const bool has_res = p.residual != nullptr && row_ok;
     const bf16* res_row = has_res ? p.residual + (size_t)row * p.ldr + (size_t)n_blk * BN : nullptr;
+    uint32_t r_next[32];
+    if (c_begin < c_end) tmem_ld32(taddr + c_begin * 32, r_next);
 #pragma unroll 1
     for (int c = c_begin; c < c_end; ++c) {
       uint32_t r[32];
-      tmem_ld32(taddr + c * 32, r);
       uint4 res_cur[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) res_cur[i] = res_pre[i];
       if (has_res && c + 1 < c_end)             // next chunk's residual: in flight while this chunk is processed
         load_res_chunk(res_row + (c + 1) * 32, res_pre, p.wide != 0);
       tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = r_next[j];
+      if (c + 1 < c_end) tmem_ld32(taddr + (c + 1) * 32, r_next);      // next chunk's accumulators: in flight during the math
       const int n0 = n_blk * BN + c * 32;
       float v[32];
 #pragma unroll
@@ -307,9 +315,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  constexpr int ACC = Cfg::ACC;
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + ACC + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * ACC);
 
+  pdl_trigger();          // the next kernel may start its prologue while this one runs (it waits before touching memory)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;       // 0 = leader (issues the MMAs)
@@ -319,7 +329,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     // accumulator drained: one arrive per epilogue warp, from both CTAs of a pair (on the leader's barrier)
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), CTA2 ? 16 : 8); }
+    for (int a = 0; a < ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), CTA2 ? 16 : 8); }
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -333,6 +343,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();             // everything above overlapped the previous kernel's tail; global data is touched only below
 
   const int total_tiles = p.tiles_m * p.tiles_n;
 
@@ -406,7 +417,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
       if constexpr (CTA2) umma_commit_2sm(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
-      acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+      if (++acc == ACC) { acc = 0; acc_phase ^= 1u; }
     }
   } else if (warp >= 2) {
     // ===================== epilogue (each CTA: its own 128 accumulator rows) =====================
@@ -414,8 +425,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = (warp - 2) >> 2;             // which half of the column chunks this warp handles
     int acc = 0; uint32_t acc_phase = 0;
     const float gate = p.gate ? __ldg(p.gate) : 1.0f;
-    const uint32_t tempty_leader0 = CTA2 ? mapa_cluster(tempty_bar(0), 0) : tempty_bar(0);
-    const uint32_t tempty_leader1 = CTA2 ? mapa_cluster(tempty_bar(1), 0) : tempty_bar(1);
+    const uint32_t tempty_leader0 = CTA2 ? mapa_cluster(tempty_bar(0), 0) : tempty_bar(0);   // consecutive stages: +8 bytes
     for (int tile = unit; tile < total_tiles; tile += num_units) {
       const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
       const int row = m_blk * ROWS_PER_TILE + (int)rank * 128 + q * 32 + lane;
@@ -442,10 +452,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        const uint32_t bar = acc ? tempty_leader1 : tempty_leader0;
+        const uint32_t bar = tempty_leader0 + 8u * acc;
         if constexpr (CTA2) mbar_arrive_cluster(bar); else mbar_arrive(bar);
       }
-      acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+      if (++acc == ACC) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
@@ -472,22 +482,14 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmK
     attr_set = true;
   }
   const int tiles = p.tiles_m * p.tiles_n;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cudaLaunchAttribute attr[1];
+  int grid;
   if (CTA2) {
     const int pairs = num_sms() / 2;
-    cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    grid = 2 * (tiles < pairs ? tiles : pairs);
   } else {
-    cfg.gridDim = dim3(tiles < num_sms() ? tiles : num_sms());
+    grid = tiles < num_sms() ? tiles : num_sms();
   }
-  cfg.blockDim = dim3(320);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cfg.stream = st;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+  cudaError_t e = launch_k(kern, dim3(grid), dim3(320), Cfg::SMEM_BYTES, st, CTA2 ? 2 : 1, ta, tb, p);
   count_launch();
   if (e != cudaSuccess) return set_error(std::string("gemm launch: ") + cudaGetErrorString(e));
   return check_launch("gemm launch");
@@ -499,7 +501,7 @@ int g_cta2_mode = -1;   // 0 = heuristic, 1 = never pair, 2 = pair whenever lega
 // Tile choice.  Per 64-wide K step an SM needs max(MMA cycles = 2*BN, operand bytes / ~42 B/clk of L2->SM
 // bandwidth) cycles; a pair stages 128 + BN/2 operand rows per SM instead of 128 + BN.  The model picks the
 // (BN, paired?) with the least waves x (cycles per K step + amortised fixed cost), preferring more CTAs on ties.
-static void pick_tile(int M, int N, int num_kb, bool geglu, int* bn_out, int* cta2_out) {
+static void pick_tile(int M, int N, int num_kb, bool geglu, bool conv, int* bn_out, int* cta2_out) {
   if (g_cta2_mode < 0) {
     const char* e = getenv("GLG_GEMM_CTA2");
     g_cta2_mode = e ? atoi(e) : 0;
@@ -509,6 +511,8 @@ static void pick_tile(int M, int N, int num_kb, bool geglu, int* bn_out, int* ct
   float best_cost = 1e30f; int best_bn = 0, best_pair = 0;
   for (int pair = 0; pair < 2; ++pair) {
     if (pair && (g_cta2_mode == 1 || M <= 128)) continue;
+    // measured on B200 (profiles/): pairing pays only for large, long-K, N % 256 == 0 problems; the 3x3 convs tie
+    if (pair && g_cta2_mode == 0 && (conv || N % 256 || num_kb < 16 || M < 2048)) continue;
     if (!pair && g_cta2_mode == 2 && M > 128) {
       bool any = false;
       for (int i = 0; i < 3; ++i) any |= (N % cands[i] == 0) && (!geglu || cands[i] == 256);
@@ -552,7 +556,7 @@ extern "C" int glg_gemm(const GlgGemmArgs* a, void* stream) {
   if (a->rowbias && ((a->ld_rowbias % 4) || a->rows_per_batch <= 0)) return set_error("glg_gemm: bad rowbias args");
   if (a->geglu && (a->N % 256 || !a->bias || a->out_fp32)) return set_error("glg_gemm: geglu needs N % 256 == 0, a bias and bf16 output");
   int bn = 0, cta2 = 0;
-  pick_tile(a->M, a->N, (a->conv_mode ? 9 : 1) * (a->K / 64), a->geglu != 0, &bn, &cta2);
+  pick_tile(a->M, a->N, (a->conv_mode ? 9 : 1) * (a->K / 64), a->geglu != 0, a->conv_mode != 0, &bn, &cta2);
   if (!bn) return set_error("glg_gemm: N must be a multiple of 64");
   GemmKParams p;
   memset(&p, 0, sizeof(p));

@@ -37,9 +37,12 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
 // Each CTA writes its per-group partial (sum, sumsq) to scratch; the last CTA of a batch (atomic ticket)
 // reduces the partials in chunk order - no floating-point atomics on the result, so a forward is
 // bit-reproducible run to run.
-// scratch layout (floats): final[B][G][2] (sum, sumsq) | partial[B][chunks][G][2] | ticket[B] (uint)
+// scratch layout (floats): ticket[64] (uint, zero before the first use, reset by the last CTA) | final[B][G][2] (sum, sumsq)
+//                          | partial[B][chunks][G][2]
 __global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ scratch,
                                 int B, int HW, int C, int groups, int rows_per_chunk) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float gn_sm[];          // [2][C]
   __shared__ bool is_last;
   float* s_sum = gn_sm;
@@ -48,9 +51,9 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float
   const int rpi = blockDim.x / vec;
   const int cv = threadIdx.x % vec, rl = threadIdx.x / vec;
   const int b = blockIdx.y, chunks = gridDim.x;
-  float* fin = scratch + (long long)b * groups * 2;
-  float* part = scratch + (long long)B * groups * 2 + ((long long)b * chunks + blockIdx.x) * groups * 2;
-  unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + (long long)B * groups * 2 * (1 + chunks)) + b;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch) + b;
+  float* fin = scratch + 64 + (long long)b * groups * 2;
+  float* part = scratch + 64 + (long long)B * groups * 2 + ((long long)b * chunks + blockIdx.x) * groups * 2;
   const int r0 = blockIdx.x * rows_per_chunk;
   const int r1 = min(HW, r0 + rows_per_chunk);
   float a[8], q[8];
@@ -100,13 +103,14 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float
   __syncthreads();
   if (is_last) {
     __threadfence();
-    const float* pb = scratch + (long long)B * groups * 2 + (long long)b * chunks * groups * 2;
+    const float* pb = scratch + 64 + (long long)B * groups * 2 + (long long)b * chunks * groups * 2;
     for (int g = threadIdx.x; g < groups; g += blockDim.x) {
       float s = 0.f, ss = 0.f;
       for (int k = 0; k < chunks; ++k) { s += __ldcg(pb + (long long)k * groups * 2 + g * 2); ss += __ldcg(pb + (long long)k * groups * 2 + g * 2 + 1); }
       fin[g * 2] = s;
       fin[g * 2 + 1] = ss;
     }
+    if (threadIdx.x == 0) *ticket = 0u;       // ready for the next GroupNorm on this scratch (stream-ordered)
   }
 }
 
@@ -117,6 +121,8 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, long long ldx, bf16*
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 const float* __restrict__ stats, int HW, int C, int groups, float eps, int silu,
                                 int rows_per_chunk) {
+  pdl_trigger();
+  pdl_wait();
   const int vec = C >> 3;
   const int rpi = blockDim.x / vec;
   const int cv = threadIdx.x % vec, rl = threadIdx.x / vec;
@@ -128,8 +134,8 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, long long ldx, bf16*
   for (int j = 0; j < 8; ++j) {
     const int c = cv * 8 + j;
     const int g = c / cpg;
-    const float mean = stats[((long long)b * groups + g) * 2] * inv_n;
-    const float var = fmaxf(stats[((long long)b * groups + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+    const float mean = stats[64 + ((long long)b * groups + g) * 2] * inv_n;
+    const float var = fmaxf(stats[64 + ((long long)b * groups + g) * 2 + 1] * inv_n - mean * mean, 0.f);
     const float ga = gamma[c] * rsqrtf(var + eps);
     sa[j] = ga;
     sb[j] = beta[c] - mean * ga;
@@ -172,6 +178,8 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, long long ldx, bf16*
 __global__ void gn_small_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 int HW, int C, int groups, float eps, int silu) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[2][32];
   const int g = blockIdx.x, b = blockIdx.y;
   const int cpg = C / groups, half = cpg >> 1;        // cpg is even: process bf16 pairs
@@ -211,6 +219,8 @@ template <int MAXV>
 __global__ void ln_kernel(const bf16* __restrict__ x, long long x_batch, bf16* __restrict__ y, long long y_batch,
                           const float* __restrict__ gamma, const float* __restrict__ beta,
                           int rows, int C, float eps, long long total_rows) {
+  pdl_trigger();
+  pdl_wait();
   const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (gw >= total_rows) return;
   const int lane = threadIdx.x & 31;
@@ -270,7 +280,7 @@ extern "C" int glg_groupnorm(const void* x, int64_t ldx, void* y, int64_t ldy, c
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (HW <= 256 && ((C / groups) % 2 == 0)) {
     dim3 grid(groups, B);
-    gn_small_kernel<<<grid, 256, 0, st>>>((const bf16*)x, ldx, (bf16*)y, ldy, gamma, beta, HW, C, groups, eps, silu);
+    launch_k(gn_small_kernel, dim3(grid), dim3(256), 0, st, 1, (const bf16*)x, ldx, (bf16*)y, ldy, gamma, beta, HW, C, groups, eps, silu);
     count_launch();
     return check_launch("gn_small launch");
   }
@@ -285,13 +295,12 @@ extern "C" int glg_groupnorm(const void* x, int64_t ldx, void* y, int64_t ldy, c
   const int rows_per_chunk = (HW + chunks - 1) / chunks;
   chunks = (HW + rows_per_chunk - 1) / rows_per_chunk;
   dim3 grid(chunks, B);
-  if ((long long)B * groups * 2 * (1 + chunks) + B > (long long)GLG_GN_SCRATCH_FLOATS(B, groups)) return set_error("glg_groupnorm: internal scratch sizing");
-  cudaError_t e = cudaMemsetAsync(stats + (long long)B * groups * 2 * (1 + chunks), 0, sizeof(unsigned int) * B, st);
-  if (e != cudaSuccess) return set_error(std::string("glg_groupnorm memset: ") + cudaGetErrorString(e));
-  gn_stats_kernel<<<grid, threads, 2 * C * sizeof(float), st>>>((const bf16*)x, ldx, stats, B, HW, C, groups, rows_per_chunk);
+  if (B > 64) return set_error("glg_groupnorm: at most 64 samples per call");
+  if (64 + (long long)B * groups * 2 * (1 + chunks) > (long long)GLG_GN_SCRATCH_FLOATS(B, groups)) return set_error("glg_groupnorm: internal scratch sizing");
+  launch_k(gn_stats_kernel, dim3(grid), dim3(threads), 2 * C * sizeof(float), st, 1, (const bf16*)x, ldx, stats, B, HW, C, groups, rows_per_chunk);
   count_launch();
   if (check_launch("gn_stats launch")) return -1;
-  gn_apply_kernel<<<grid, threads, 0, st>>>((const bf16*)x, ldx, (bf16*)y, ldy, gamma, beta, stats, HW, C, groups, eps, silu, rows_per_chunk);
+  launch_k(gn_apply_kernel, dim3(grid), dim3(threads), 0, st, 1, (const bf16*)x, ldx, (bf16*)y, ldy, gamma, beta, stats, HW, C, groups, eps, silu, rows_per_chunk);
   count_launch();
   return check_launch("gn_apply launch");
 }
@@ -305,9 +314,9 @@ extern "C" int glg_layernorm(const void* x, int64_t x_batch, void* y, int64_t y_
   const int wpb = 8;
   const unsigned grid = (unsigned)((total + wpb - 1) / wpb);
   const int vec = C / 8;
-  if (vec <= 64) ln_kernel<2><<<grid, wpb * 32, 0, st>>>((const bf16*)x, x_batch, (bf16*)y, y_batch, gamma, beta, rows, C, eps, total);
-  else if (vec <= 160) ln_kernel<5><<<grid, wpb * 32, 0, st>>>((const bf16*)x, x_batch, (bf16*)y, y_batch, gamma, beta, rows, C, eps, total);
-  else ln_kernel<8><<<grid, wpb * 32, 0, st>>>((const bf16*)x, x_batch, (bf16*)y, y_batch, gamma, beta, rows, C, eps, total);
+  if (vec <= 64) launch_k(ln_kernel<2>, dim3(grid), dim3(wpb * 32), 0, st, 1, (const bf16*)x, x_batch, (bf16*)y, y_batch, gamma, beta, rows, C, eps, total);
+  else if (vec <= 160) launch_k(ln_kernel<5>, dim3(grid), dim3(wpb * 32), 0, st, 1, (const bf16*)x, x_batch, (bf16*)y, y_batch, gamma, beta, rows, C, eps, total);
+  else launch_k(ln_kernel<8>, dim3(grid), dim3(wpb * 32), 0, st, 1, (const bf16*)x, x_batch, (bf16*)y, y_batch, gamma, beta, rows, C, eps, total);
   count_launch();
   return check_launch("layernorm launch");
 }

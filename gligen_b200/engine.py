@@ -278,7 +278,7 @@ class Engine:
         sz = self._sizes(Bt, N, nctx)
         B_ = {k: self._buf(v, torch.float32 if k == "xstat" else None) for k, v in sz.items()}
         B_["blk2"] = self._buf(sz["blk"])
-        stats = self._buf(2 * 32 * (Bt + 4 * 148 + 2 * Bt) + Bt + 64, torch.float32)   # GLG_GN_SCRATCH_FLOATS
+        stats = torch.zeros(2 * 32 * (Bt + 4 * 148 + 2 * Bt) + Bt + 64, device=self.dev, dtype=torch.float32)   # GLG_GN_SCRATCH_FLOATS, tickets zeroed once
         Himg = cfg.image_size
         f32 = torch.float32
 

@@ -110,8 +110,8 @@ int glg_attention(const GlgAttnArgs* args, void* stream);
  * GroupNorm over channels-last input (32 groups in the reference): fp32 statistics, affine, optional
  * SiLU, bf16 out.  Replaces GroupNorm32+SiLU (util.py:208-226, openaimodel.py:155-156,179-180,392-393;
  * eps 1e-5) and Normalize (attention.py:76-77; eps 1e-6, no SiLU).  `stats` is a caller-provided fp32
- * scratch of GLG_GN_SCRATCH_FLOATS(B, groups) floats (per-CTA partials reduced in a fixed order: results are
- * bit-reproducible run to run).
+ * scratch of GLG_GN_SCRATCH_FLOATS(B, groups) floats whose first 64 words must be ZERO before the first call (they
+ * hold self-resetting tickets; per-CTA partials are reduced in a fixed order: results are bit-reproducible). B <= 64.
  */
 #define GLG_GN_SCRATCH_FLOATS(B, groups) (2 * (groups) * ((B) + 4 * 148 + 2 * (B)) + (B) + 64)
 int glg_groupnorm(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma, const float* beta,
