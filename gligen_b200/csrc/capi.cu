@@ -25,7 +25,7 @@ bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("GLG_PDL");
-    v = e ? (atoi(e) != 0) : 1;
+    v = e ? (atoi(e) != 0) : 0;     // measured on B200: no gain for this launch mix (profiles/), so opt-in
   }
   return v != 0;
 }

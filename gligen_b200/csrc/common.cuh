@@ -15,7 +15,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
 // ------------------------------------------------------------------ programmatic dependent launch (PDL)
-// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel
+// With GLG_PDL=1 every kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel
 // in the stream may be scheduled (and run its prologue: barrier init, TMEM alloc, descriptor prefetch) while this
 // one drains; pdl_wait() blocks until the previous grid has completed and its memory is visible, so it must precede
 // the first access to global data.  Without the launch attribute both are no-ops.

@@ -49,6 +49,9 @@ struct GemmKParams {
   // batch-strided output rows: address = (row / orpb) * obs + (row % orpb) * ldc   (orpb == 0: uniform rows)
   int orpb; long long obs;
   int wide;                       // 1: rows of out / residual are 32-byte aligned -> 256-bit global accesses
+  // split-K: `splits` CTAs share one output tile, each reducing a contiguous range of K steps into its own fp32
+  // slab ws[split][M][N]; splitk_reduce_kernel sums the slabs in a fixed order and applies the epilogue.
+  int splits; float* ws;
 };
 
 template <int BN, bool CTA2> struct GemmCfg {
@@ -303,6 +306,73 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
   }
 }
 
+// split-K: raw fp32 accumulators -> ws[split][row][n]
+template <int BN>
+__device__ __forceinline__ void epilogue_partial(const GemmKParams& p, uint32_t taddr, int row, int n_blk, int half, int split) {
+  constexpr int NCH = BN / 32;
+  const int c_begin = half ? (NCH + 1) / 2 : 0, c_end = half ? NCH : (NCH + 1) / 2;
+  float* dst = p.ws + ((size_t)split * p.M + row) * p.N + (size_t)n_blk * BN;
+#pragma unroll 1
+  for (int c = c_begin; c < c_end; ++c) {
+    uint32_t r[32];
+    tmem_ld32(taddr + c * 32, r);
+    tmem_ld_wait();
+    if (row < p.M) {
+      float4* o4 = reinterpret_cast<float4*>(dst + c * 32);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        o4[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+    }
+  }
+}
+
+// out[row][n..n+7] = sum_s ws[s][row][n..] (fixed order) + bias + rowbias, SiLU, gate, + residual  -> bf16
+__global__ void splitk_reduce_kernel(const GemmKParams p) {
+  pdl_trigger();
+  pdl_wait();
+  const int nv = p.N >> 3;
+  const long long total = (long long)p.M * nv;
+  const float gate = p.gate ? __ldg(p.gate) : 1.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(i / nv), n0 = (int)(i % nv) * 8;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < p.splits; ++s) {
+      const float4* w4 = reinterpret_cast<const float4*>(p.ws + ((size_t)s * p.M + row) * p.N + n0);
+      const float4 a = w4[0], b = w4[1];
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += __ldg(p.bias + n0 + j);
+    }
+    if (p.rowbias) {
+      const float* rb = p.rowbias + (size_t)(row / p.rows_per_batch) * p.ld_rowbias + n0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += __ldg(rb + j);
+    }
+    if (p.act == GLG_ACT_SILU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+    }
+    if (p.gate) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= gate;
+    }
+    if (p.residual) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + n0));
+      float2 f;
+      f = unpack_bf16x2(u.x); v[0] += f.x; v[1] += f.y;
+      f = unpack_bf16x2(u.y); v[2] += f.x; v[3] += f.y;
+      f = unpack_bf16x2(u.z); v[4] += f.x; v[5] += f.y;
+      f = unpack_bf16x2(u.w); v[6] += f.x; v[7] += f.y;
+    }
+    const size_t out_off = p.orpb ? (size_t)(row / p.orpb) * p.obs + (size_t)(row % p.orpb) * p.ldc : (size_t)row * p.ldc;
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]); o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + out_off + n0) = o;
+  }
+}
+
 template <int BN, bool GEGLU, bool CTA2>
 __global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
@@ -345,12 +415,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   pdl_wait();             // everything above overlapped the previous kernel's tail; global data is touched only below
 
-  const int total_tiles = p.tiles_m * p.tiles_n;
+  const int total_work = p.tiles_m * p.tiles_n * p.splits;
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer (every CTA loads its own 128 rows of A and its share of B) ==========
     int stage = 0; uint32_t phase = 0;
-    for (int tile = unit; tile < total_tiles; tile += num_units) {
+    for (int work = unit; work < total_work; work += num_units) {
+      const int tile = work / p.splits, split = work - tile * p.splits;
+      const int kb_lo = (split * p.num_kb) / p.splits, kb_n = ((split + 1) * p.num_kb) / p.splits - kb_lo;
       const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
       const int row0 = m_blk * ROWS_PER_TILE + (int)rank * 128;
       int b0 = 0, y0 = 0;
@@ -362,8 +434,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // K steps are visited in a per-tile rotated order: tiles running at the same time would otherwise request
       // the very same weight (and activation) lines from L2 in lockstep; the rotation spreads them over slices.
       // (fp32 accumulation order depends only on the tile index -> results stay reproducible.)
-      int kb = (int)(((unsigned)tile * 3u) % (unsigned)p.num_kb);
-      for (int it = 0; it < p.num_kb; ++it, kb = (kb + 1 == p.num_kb) ? 0 : kb + 1) {
+      int kb = kb_lo + (int)(((unsigned)tile * 3u) % (unsigned)kb_n);
+      for (int it = 0; it < kb_n; ++it, kb = (kb + 1 == kb_lo + kb_n) ? kb_lo : kb + 1) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         // the leader's barrier collects the bytes of both CTAs
         if (!CTA2) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
@@ -398,11 +470,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 256 : 128, BN);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = unit; tile < total_tiles; tile += num_units) {
+    for (int work = unit; work < total_work; work += num_units) {
+      const int split = work % p.splits;
+      const int kb_n = ((split + 1) * p.num_kb) / p.splits - (split * p.num_kb) / p.splits;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      for (int kb = 0; kb < kb_n; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         const uint32_t a_addr = base + stage * Cfg::STAGE_BYTES;
@@ -426,7 +500,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0; uint32_t acc_phase = 0;
     const float gate = p.gate ? __ldg(p.gate) : 1.0f;
     const uint32_t tempty_leader0 = CTA2 ? mapa_cluster(tempty_bar(0), 0) : tempty_bar(0);   // consecutive stages: +8 bytes
-    for (int tile = unit; tile < total_tiles; tile += num_units) {
+    for (int work = unit; work < total_work; work += num_units) {
+      const int tile = work / p.splits, split = work - tile * p.splits;
       const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
       const int row = m_blk * ROWS_PER_TILE + (int)rank * 128 + q * 32 + lane;
       // ---- prefetch what does not depend on the accumulator: LayerNorm statistics and the first residual chunk
@@ -448,7 +523,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      epilogue_tile<BN, GEGLU>(p, taddr, row, n_blk, half, gate, ln_mu, ln_rstd, res_pre);
+      if (p.splits > 1) epilogue_partial<BN>(p, taddr, row, n_blk, half, split);
+      else epilogue_tile<BN, GEGLU>(p, taddr, row, n_blk, half, gate, ln_mu, ln_rstd, res_pre);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -481,7 +557,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmK
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(gemm): ") + cudaGetErrorString(e));
     attr_set = true;
   }
-  const int tiles = p.tiles_m * p.tiles_n;
+  const int tiles = p.tiles_m * p.tiles_n * p.splits;
   int grid;
   if (CTA2) {
     const int pairs = num_sms() / 2;
@@ -492,23 +568,36 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmK
   cudaError_t e = launch_k(kern, dim3(grid), dim3(320), Cfg::SMEM_BYTES, st, CTA2 ? 2 : 1, ta, tb, p);
   count_launch();
   if (e != cudaSuccess) return set_error(std::string("gemm launch: ") + cudaGetErrorString(e));
-  return check_launch("gemm launch");
+  if (check_launch("gemm launch")) return -1;
+  if (p.splits > 1) {
+    const long long total = (long long)p.M * (p.N / 8);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    e = launch_k(splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), 0, st, 1, p);
+    count_launch();
+    if (e != cudaSuccess) return set_error(std::string("splitk reduce launch: ") + cudaGetErrorString(e));
+    return check_launch("splitk reduce launch");
+  }
+  return 0;
 }
 
-int g_force_bn = 0;     // test hooks (glg_debug_force_bn / glg_debug_gemm_cta2)
+int g_force_bn = 0;     // test hooks (glg_debug_force_bn / glg_debug_gemm_cta2 / glg_debug_splitk)
+int g_splitk_mode = 0;  // 0 = heuristic, 1 = never, 2 = split whenever legal
 int g_cta2_mode = -1;   // 0 = heuristic, 1 = never pair, 2 = pair whenever legal; -1 = read GLG_GEMM_CTA2 (default 0)
 
-// Tile choice.  Per 64-wide K step an SM needs max(MMA cycles = 2*BN, operand bytes / ~42 B/clk of L2->SM
-// bandwidth) cycles; a pair stages 128 + BN/2 operand rows per SM instead of 128 + BN.  The model picks the
-// (BN, paired?) with the least waves x (cycles per K step + amortised fixed cost), preferring more CTAs on ties.
-static void pick_tile(int M, int N, int num_kb, bool geglu, bool conv, int* bn_out, int* cta2_out) {
+// Tile / split choice by a small time model (cycles):
+//   per 64-wide K step an SM needs max(MMA = 2*BN, operand bytes / ~42 B/clk of L2->SM bandwidth) cycles (a pair
+//   stages 128 + BN/2 operand rows per SM instead of 128 + BN); a CTA pays ~3000 cycles of fixed cost per work item;
+//   split-K adds a reduce pass over splits * M * N fp32.  The least estimated time wins.
+static void pick_tile(int M, int N, int num_kb, bool geglu, bool conv, int max_splits, long long ws_bytes,
+                      int* bn_out, int* cta2_out, int* splits_out) {
   if (g_cta2_mode < 0) {
     const char* e = getenv("GLG_GEMM_CTA2");
     g_cta2_mode = e ? atoi(e) : 0;
   }
   const int sms = num_sms();
   const int cands[4] = {256, 160, 128, 64};
-  float best_cost = 1e30f; int best_bn = 0, best_pair = 0;
+  float best = 1e30f; int best_bn = 0, best_pair = 0, best_s = 1;
   for (int pair = 0; pair < 2; ++pair) {
     if (pair && (g_cta2_mode == 1 || M <= 128)) continue;
     // measured on B200 (profiles/): pairing pays only for large, long-K, N % 256 == 0 problems; the 3x3 convs tie
@@ -524,20 +613,28 @@ static void pick_tile(int M, int N, int num_kb, bool geglu, bool conv, int* bn_o
       if (geglu && bn != 256) continue;
       if (g_force_bn && bn != g_force_bn && (N % g_force_bn == 0) && !geglu) continue;
       if (pair && bn < 128) continue;                    // per-CTA half of B must stay a whole number of KiB
+      if (pair && g_cta2_mode == 0 && bn != 256) continue;
       const int rows = pair ? 256 : 128;
       const int tiles = ((M + rows - 1) / rows) * (N / bn);
       const int units = pair ? sms / 2 : sms;
-      const int waves = (tiles + units - 1) / units;
       const float mma = 2.0f * bn;
       const float l2 = 3.05f * (pair ? 128.0f + 0.5f * bn : 128.0f + bn);
-      const float per_kb = (mma > l2 ? mma : l2) + 3000.0f / (float)num_kb;
-      float cost = (float)waves * per_kb;
-      const int ctas = (pair ? 2 : 1) * (tiles < units ? tiles : units);
-      cost *= 1.0f + 0.10f * (1.0f - (float)ctas / (float)sms);     // idle SMs: prefer the finer decomposition
-      if (cost < best_cost) { best_cost = cost; best_bn = bn; best_pair = pair; }
+      const float per_kb = mma > l2 ? mma : l2;
+      for (int sp = 1; sp <= (pair ? 1 : max_splits); ++sp) {
+        if (sp > 1 && (num_kb / sp < 4 || (long long)sp * M * N * 4 > ws_bytes)) break;
+        if (sp > 1 && tiles * 2 > units && g_splitk_mode != 2) break;        // only when the tile grid leaves >= half the SMs idle
+        if (g_splitk_mode == 2 && max_splits > 1 && sp == 1 && num_kb >= 8) continue;      // test hook: force a split
+        const int waves = (tiles * sp + units - 1) / units;
+        const int kb_cta = (num_kb + sp - 1) / sp;
+        float t = (float)waves * (per_kb * kb_cta + 3000.0f);
+        if (sp > 1) t += 5000.0f + (float)sp * M * N * 4.0f / (sms * 40.0f);
+        const int ctas = (pair ? 2 : 1) * (tiles * sp < units ? tiles * sp : units);
+        t *= 1.0f + 0.10f * (1.0f - (float)ctas / (float)sms);     // idle SMs: prefer the finer decomposition
+        if (t < best) { best = t; best_bn = bn; best_pair = pair; best_s = sp; }
+      }
     }
   }
-  *bn_out = best_bn; *cta2_out = best_pair;
+  *bn_out = best_bn; *cta2_out = best_pair; *splits_out = best_s;
 }
 
 }  // namespace glg
@@ -546,6 +643,7 @@ using namespace glg;
 
 extern "C" void glg_debug_force_bn(int bn) { glg::g_force_bn = bn; }
 extern "C" void glg_debug_gemm_cta2(int mode) { glg::g_cta2_mode = mode; }
+extern "C" void glg_debug_splitk(int mode) { glg::g_splitk_mode = mode; }
 
 extern "C" int glg_gemm(const GlgGemmArgs* a, void* stream) {
   if (!a) return set_error("glg_gemm: null args");
@@ -555,8 +653,11 @@ extern "C" int glg_gemm(const GlgGemmArgs* a, void* stream) {
   if (((uintptr_t)a->A | (uintptr_t)a->W | (uintptr_t)a->out | (uintptr_t)a->residual) & 15) return set_error("glg_gemm: pointers must be 16-byte aligned");
   if (a->rowbias && ((a->ld_rowbias % 4) || a->rows_per_batch <= 0)) return set_error("glg_gemm: bad rowbias args");
   if (a->geglu && (a->N % 256 || !a->bias || a->out_fp32)) return set_error("glg_gemm: geglu needs N % 256 == 0, a bias and bf16 output");
-  int bn = 0, cta2 = 0;
-  pick_tile(a->M, a->N, (a->conv_mode ? 9 : 1) * (a->K / 64), a->geglu != 0, a->conv_mode != 0, &bn, &cta2);
+  int bn = 0, cta2 = 0, splits = 1;
+  const bool can_split = a->splitk_ws && g_splitk_mode != 1 && !a->geglu && !a->ln_stats && !a->stats_out && !a->out_fp32 &&
+                         !((uintptr_t)a->splitk_ws & 15);
+  pick_tile(a->M, a->N, (a->conv_mode ? 9 : 1) * (a->K / 64), a->geglu != 0, a->conv_mode != 0, can_split ? 8 : 1,
+            a->splitk_ws_bytes, &bn, &cta2, &splits);
   if (!bn) return set_error("glg_gemm: N must be a multiple of 64");
   GemmKParams p;
   memset(&p, 0, sizeof(p));
@@ -587,6 +688,9 @@ extern "C" int glg_gemm(const GlgGemmArgs* a, void* stream) {
   if (a->bias && ((uintptr_t)a->bias & 15)) return set_error("glg_gemm: bias must be 16-byte aligned");
   p.wide = !a->out_fp32 && !((uintptr_t)a->out & 31) && !(a->ldc % 16) && !(a->out_batch_stride % 16) &&
            (!a->residual || (!((uintptr_t)a->residual & 31) && !(a->ldr % 16)));
+
+  p.splits = splits;
+  p.ws = splits > 1 ? reinterpret_cast<float*>(a->splitk_ws) : nullptr;
 
   const uint32_t brows = (uint32_t)(cta2 ? bn / 2 : bn);
   CUtensorMap ta, tb;

@@ -16,7 +16,7 @@ int check_launch(const char* what);
 // arguments).  dims/box innermost first; strides in BYTES for dims 1..rank-1.  Returns 0 or records the error.
 int get_tmap_bf16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box);
 int num_sms();
-bool pdl_enabled();     // GLG_PDL env (default on)
+bool pdl_enabled();     // GLG_PDL env (default off: measured neutral-to-negative for this launch mix)
 
 // Launch with programmatic dependent launch (and optionally a thread-block cluster along x).
 template <typename... KArgs, typename... Args>

@@ -24,6 +24,7 @@ class GlgGemmArgs(C.Structure):
         ("geglu", c_int), ("conv_mode", c_int), ("H", c_int), ("Wd", c_int), ("Bn", c_int),
         ("ln_stats", c_void_p), ("ln_colsum", c_void_p), ("ln_slots", c_int), ("ln_eps", c_float),
         ("stats_out", c_void_p), ("stats_slots", c_int), ("out_rows_per_batch", c_int), ("out_batch_stride", c_int64),
+        ("splitk_ws", c_void_p), ("splitk_ws_bytes", c_int64),
     ]
 
 
@@ -61,7 +62,7 @@ SIGNATURES = {
                                    c_float, c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 # not part of the public header: test hook
-_DEBUG_SIGNATURES = {"glg_debug_force_bn": (None, [c_int]), "glg_debug_attn_mode": (None, [c_int]), "glg_debug_attn_poly": (None, [c_int]), "glg_debug_gemm_cta2": (None, [c_int])}
+_DEBUG_SIGNATURES = {"glg_debug_force_bn": (None, [c_int]), "glg_debug_attn_mode": (None, [c_int]), "glg_debug_attn_poly": (None, [c_int]), "glg_debug_gemm_cta2": (None, [c_int]), "glg_debug_splitk": (None, [c_int])}
 
 _lib: Optional[C.CDLL] = None
 

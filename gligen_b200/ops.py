@@ -46,6 +46,8 @@ class CudaOps:
             raise L.GligenLibraryError("CudaOps needs a CUDA device (there is no CPU fallback)")
         self.lib = L.load()
         self.trace = None          # set to a list to record (kind, algorithmic flops, algorithmic bytes) per op call
+        # fp32 scratch for split-K GEMMs (8 slabs of the largest small-M output: 8 x 1024 x 2560 floats = 80 MiB)
+        self.splitk_ws = torch.empty(8 * 1024 * 2560, device=self.device, dtype=torch.float32)
 
     def _note(self, kind, flops=0.0, nbytes=0.0):
         if self.trace is not None:
@@ -115,6 +117,7 @@ class CudaOps:
             g.stats_out, g.stats_slots = stats_out.data_ptr(), stats_out.shape[1]
         else:
             g.stats_out, g.stats_slots = None, 0
+        g.splitk_ws, g.splitk_ws_bytes = self.splitk_ws.data_ptr(), self.splitk_ws.numel() * 4
         L.check(self.lib.glg_gemm(C.byref(g), self._stream()), "glg_gemm")
         taps = 9 if conv is not None else 1
         self._note("conv3x3" if conv is not None else "gemm", 2.0 * M * N * K * taps,

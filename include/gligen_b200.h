@@ -58,6 +58,9 @@ void glg_reset_launch_count(void);
  *   (stats_out[M][N/32][2]: one partial per (row, 32-column chunk) of the bf16-rounded stored values - a layout
  *   independent of the tile shape, so results are bit-reproducible).  No LayerNorm kernel, no normalised copy in HBM.
  * out_rows_per_batch > 0: output row r is written at (r / orpb) * out_batch_stride + (r % orpb) * ldc.
+ * splitk_ws: when the tile grid would leave most SMs idle (M = 64 * batch at the 8x8 level) up to 8 CTAs share an
+ *   output tile, each reducing a contiguous K range into an fp32 slab; a second kernel sums the slabs in a fixed
+ *   order and applies the epilogue (deterministic).
  */
 typedef struct GlgGemmArgs {
   const void* A;          /* bf16 */
@@ -86,6 +89,8 @@ typedef struct GlgGemmArgs {
   int32_t stats_slots;
   int32_t out_rows_per_batch;
   int64_t out_batch_stride;
+  void* splitk_ws;        /* optional fp32 scratch for split-K (small-M, long-K problems); NULL disables it */
+  int64_t splitk_ws_bytes;
 } GlgGemmArgs;
 int glg_gemm(const GlgGemmArgs* args, void* stream);
 

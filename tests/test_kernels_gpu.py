@@ -133,6 +133,31 @@ def _ln_fold_case(ops, ref, M, N, K, geglu):
     assert_close(out, y, what=f"ln-fold gemm {M}x{N}x{K} geglu={geglu}")
 
 
+@pytest.mark.parametrize("M,N,K,conv", [(512, 1280, 1280, None), (512, 1280, 5120, None), (200, 640, 2560, None),
+                                         (512, 1280, 1280, (8, 8, 8)), (128, 1280, 2560, (2, 8, 8)), (512, 256, 256, (8, 8, 8))])
+def test_gemm_split_k(ops, ref, M, N, K, conv):
+    """forced split-K (fp32 slabs + fixed-order reduce) against the unsplit statement; twice -> bit-reproducible."""
+    a = rnd(conv[0], conv[1] * conv[2], K) if conv else rnd(M, K)
+    w = rnd((9 if conv else 1) * N, K, scale=((9 if conv else 1) * K) ** -0.5, seed=1)
+    bias = rnd(N, seed=2, dtype=torch.float32)
+    res = rnd(M, N, seed=3)
+    rowbias = rnd(M // 64, N, seed=4, dtype=torch.float32) if M % 64 == 0 else None
+    outs = []
+    ops.lib.glg_debug_splitk(2)
+    try:
+        for _ in range(2):
+            out = torch.zeros(M, N, device="cuda:0", dtype=torch.bfloat16)
+            ops.gemm(a, w, out, bias=bias, rowbias=rowbias, rows_per_batch=64, residual=res, conv=conv)
+            torch.cuda.synchronize()
+            outs.append(out)
+    finally:
+        ops.lib.glg_debug_splitk(0)
+    out_r = torch.zeros(M, N, device="cuda:0", dtype=torch.bfloat16)
+    ref.gemm(a, w, out_r, bias=bias, rowbias=rowbias, rows_per_batch=64, residual=res, conv=conv)
+    assert_close(outs[0], out_r, what=f"split-K gemm {M}x{N}x{K} conv={conv}")
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_gemm_batch_strided_output(ops, ref):
     B, T, G, C = 3, 200, 30, 320
     a = rnd(B * T, C)
