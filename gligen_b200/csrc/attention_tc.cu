@@ -1,5 +1,6 @@
-// tcgen05 / TMEM flash attention for head dims <= 64 (the 64x64-latent level, d_head = 40, carries 88 % of
-// the attention FLOPs).
+// tcgen05 / TMEM flash attention for head dims <= 128 (d_head = 40 at the 64x64-latent level carries 88 % of the
+// attention FLOPs, d_head = 80 at 32x32 most of the rest).  Head dims above 64 use two 64-column
+// swizzle atoms per operand tile.
 //
 //   per CTA: one (batch, head, 128-query tile); key/value tiles of 64 keys stream through a TMA ring.
 //   warp 0 lane 0 : TMA producer (Q once, then K_j / V_j tiles; 4-D tensor maps {d, head, row, batch},
@@ -11,9 +12,9 @@
 //                                O only when the max grows by > 2^8) -> exp2 -> P_j bf16 -> tcgen05.st.
 //                                8 warps x 2 resident CTAs = 4 softmax warps per SM sub-partition, so TMEM
 //                                reads (64 B/clk/SM) and exp2 (16/clk/SM) - equal cost per score - overlap.
-//   TMEM (256 columns): S[2] (2 x 64 fp32) | P[2] (2 x 32 packed bf16) | O (<= 64 fp32).  S and P are double
-//   buffered so QK^T of tile j+1 overlaps the softmax of tile j; two CTAs are resident per SM so the
-//   exp2 (MUFU) pipe - the real bound at d = 40 - stays busy while the other CTA waits on its MMAs.
+//   TMEM (256 columns): S[2] (2 x 64 fp32; P_j, 32 packed-bf16 columns, overwrites the first half of S_j once both
+//   warps of a row pair hold their scores in registers) | O (<= 128 fp32).  S is double buffered so QK^T of tile
+//   j+1 overlaps the softmax of tile j; two CTAs are resident per SM.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -33,13 +34,18 @@ struct AttnTcParams {
 
 namespace atc {
 constexpr int BM = 128, BN = 64;
-constexpr int Q_BYTES = BM * 64 * 2;        // 16 KB
-constexpr int KV_BYTES = BN * 64 * 2;       // 8 KB each for K and V
-constexpr int STAGES = 4;
-constexpr int XCH_BYTES = 2 * 2 * 128 * 4;   // [parity][column half][row] partial maxima / sums
-constexpr int SMEM_BYTES = Q_BYTES + STAGES * 2 * KV_BYTES + 1024 + 256 + XCH_BYTES;
+constexpr int QA_BYTES = BM * 64 * 2;       // one 64-column atom of Q: 16 KB
+constexpr int KVA_BYTES = BN * 64 * 2;      // one atom of K or V: 8 KB
+constexpr int XCH_BYTES = 2 * 2 * 128 * 4;  // [parity][column half][row] partial maxima / sums
 constexpr int TMEM_COLS = 256;
-constexpr int S_COL = 0, P_COL = 128, O_COL = 192;
+constexpr int S_COL = 0, O_COL = 128;       // P_j lives in the first 32 columns of S_j
+template <int DPAD> struct Cfg {
+  static constexpr int NATOM = (DPAD + 63) / 64;
+  static constexpr int STAGES = NATOM == 1 ? 4 : 2;
+  static constexpr int Q_BYTES = NATOM * QA_BYTES;
+  static constexpr int KV_BYTES = NATOM * KVA_BYTES;          // K (or V) of one stage
+  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * 2 * KV_BYTES + 1024 + 256 + XCH_BYTES;
+};
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
 }  // namespace atc
 
@@ -49,29 +55,18 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, |f| <= 0.5, 2^f by an own degree-3
-// fit (max rel. error 7.5e-5, well below the bf16 rounding of P), exponent patched in with integer adds.
-// Used for every POLY-th probability so the MUFU pipe (16 exp2/clk/SM, the bound at d_head = 40) is relieved.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -120.0f);
-  const float t = x + 12582912.0f;               // 1.5 * 2^23: integer part lands in the low mantissa bits
-  const float f = x - (t - 12582912.0f);
-  float pl = fmaf(0.0551716685295105f, f, 0.2426111251115799f);
-  pl = fmaf(pl, f, 0.6932609677314758f);
-  pl = fmaf(pl, f, 0.9999280571937561f);
-  return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));
-}
-
-template <int DPAD, int POLY>   // DPAD: head dim rounded up to a multiple of 16 (<= 64); POLY: 0 = all MUFU, k = every k-th via ex2_poly
+template <int DPAD>   // head dim rounded up to a multiple of 16 (<= 128)
 __global__ void __launch_bounds__(320, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
   using namespace atc;
+  using C = Cfg<DPAD>;
+  constexpr int NATOM = C::NATOM, STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base;
-  const uint32_t sKV = base + Q_BYTES;
-  const uint32_t bar_base = sKV + STAGES * 2 * KV_BYTES;
+  const uint32_t sKV = base + C::Q_BYTES;              // per stage: K atoms | V atoms
+  const uint32_t bar_base = sKV + STAGES * 2 * C::KV_BYTES;
   const uint32_t q_full = bar_base;
   auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
   auto kv_empty = [&](int s) { return bar_base + 8u * (1 + STAGES + s); };
@@ -110,31 +105,39 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
-    mbar_arrive_expect_tx(q_full, Q_BYTES);
-    tma_load_4d(sQ, &tmQ, q_full, 0, h, q0, b);
+    mbar_arrive_expect_tx(q_full, C::Q_BYTES);
+#pragma unroll
+    for (int a = 0; a < NATOM; ++a) tma_load_4d(sQ + a * QA_BYTES, &tmQ, q_full, 64 * a, h, q0, b);
     int stage = 0; uint32_t phase = 0;
     for (int j = 0; j < nkt; ++j) {
       mbar_wait(kv_empty(stage), phase ^ 1u);
-      mbar_arrive_expect_tx(kv_full(stage), 2 * KV_BYTES);
-      tma_load_4d(sKV + stage * 2 * KV_BYTES, &tmK, kv_full(stage), 0, h, j * BN, b);
-      tma_load_4d(sKV + stage * 2 * KV_BYTES + KV_BYTES, &tmV, kv_full(stage), 0, h, j * BN, b);
+      mbar_arrive_expect_tx(kv_full(stage), 2 * C::KV_BYTES);
+      const uint32_t sk = sKV + stage * 2 * C::KV_BYTES, sv = sk + C::KV_BYTES;
+#pragma unroll
+      for (int a = 0; a < NATOM; ++a) {
+        tma_load_4d(sk + a * KVA_BYTES, &tmK, kv_full(stage), 64 * a, h, j * BN, b);
+        tma_load_4d(sv + a * KVA_BYTES, &tmV, kv_full(stage), 64 * a, h, j * BN, b);
+      }
       if (++stage == STAGES) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, BN);            // S = Q K^T : N = 64 keys
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, DPAD, true);    // O += P V  : N = DPAD, B (V) is MN-major
-    const uint64_t qdesc = umma_desc_kmajor_sw128(sQ);
     mbar_wait(q_full, 0);
     tc_fence_after();
     auto issue_qk = [&](int j) {
       const int stage = j % STAGES;
       mbar_wait(kv_full(stage), (uint32_t)((j / STAGES) & 1));
       tc_fence_after();
-      const uint64_t kdesc = umma_desc_kmajor_sw128(sKV + stage * 2 * KV_BYTES);
+      const uint32_t sk = sKV + stage * 2 * C::KV_BYTES;
       const uint32_t d_tmem = tmem_base + S_COL + (j & 1) * BN;
 #pragma unroll
-      for (int k = 0; k < DPAD / 16; ++k) umma_bf16(d_tmem, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+      for (int kk = 0; kk < DPAD / 16; ++kk) {        // 16 head-dim columns per step: atom kk/4, +32 B inside the atom
+        const uint64_t qd = umma_desc_kmajor_sw128(sQ + (kk >> 2) * QA_BYTES) + 2 * (kk & 3);
+        const uint64_t kd = umma_desc_kmajor_sw128(sk + (kk >> 2) * KVA_BYTES) + 2 * (kk & 3);
+        umma_bf16(d_tmem, qd, kd, idesc_s, kk != 0 ? 1u : 0u);
+      }
       umma_commit(s_full(j & 1));
     };
     issue_qk(0);
@@ -143,8 +146,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int stage = j % STAGES, bsel = j & 1;
       mbar_wait(p_full(bsel), (uint32_t)((j >> 1) & 1));
       tc_fence_after();
-      const uint64_t vdesc = umma_desc_mnmajor_sw128(sKV + stage * 2 * KV_BYTES + KV_BYTES);
-      const uint32_t a_tmem = tmem_base + P_COL + bsel * (BN / 2);
+      // V tile: [64 keys][DPAD cols] as NATOM atoms of 64 columns, KVA_BYTES apart (LBO); MN-major B operand
+      const uint64_t vdesc = umma_desc_mnmajor_sw128(sKV + stage * 2 * C::KV_BYTES + C::KV_BYTES, KVA_BYTES);
+      const uint32_t a_tmem = tmem_base + S_COL + bsel * BN;           // P_j aliases the first 32 columns of S_j
 #pragma unroll
       for (int k = 0; k < BN / 16; ++k)           // 16 keys per step: +8 TMEM columns of P, +16 rows (2048 B) of V
         umma_bf16_ts(tmem_base + O_COL, a_tmem + 8 * k, vdesc + 128 * k, idesc_o, (j | k) != 0 ? 1u : 0u);
@@ -180,13 +184,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       float mx = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
-      // row max = max over both column halves: exchange through smem with the partner warp (same rows)
+      // row max over both column halves: exchange through smem with the partner warp (same rows).  After this
+      // barrier BOTH warps hold their scores in registers, so P may overwrite the S columns.
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch_addr(bsel, hc, rloc)), "f"(mx) : "memory");
       pair_sync();
       float other;
       asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch_addr(bsel, hc ^ 1, rloc)) : "memory");
       mx = fmaxf(mx, other);
-      // O (and the P buffer about to be overwritten) are stable once PV_{j-1} has completed
+      // O (and the P/S buffer of tile j-2) are stable once PV_{j-1} has completed
       if (j > 0) {
         mbar_wait(pv_done(bsel ^ 1), (uint32_t)(((j - 1) >> 1) & 1));
         tc_fence_after();
@@ -217,15 +222,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       float sum = 0.f;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float x0 = fmaf(__uint_as_float(sv[2 * i]), sl2, -ms);
-        const float x1 = fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -ms);
-        const float a0 = ex2_approx(x0);
-        const float a1 = (POLY != 0 && ((2 * i + 1) % (POLY ? POLY : 1)) == POLY - 1) ? ex2_poly(x1) : ex2_approx(x1);
+        const float a0 = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), sl2, -ms));
+        const float a1 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -ms));
         sum += a0 + a1;
         pk[i] = pack_bf16x2(a0, a1);
       }
       l += sum;
-      tmem_st16(lane_base + P_COL + bsel * (BN / 2) + hc * 16, pk);
+      tmem_st16(lane_base + S_COL + bsel * BN + hc * 16, pk);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_full(bsel));
@@ -271,35 +274,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
-int g_attn_poly = 0;   // measured on B200: all-MUFU is fastest (the kernel is not MUFU-bound); 2 / 4 = every 2nd / 4th exp2 on the FMA pipe (glg_debug_attn_poly)
-
-template <int DPAD, int POLY>
-static int launch_attn_tc2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p, int B, cudaStream_t st) {
+template <int DPAD>
+static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p, int B, cudaStream_t st) {
   static bool attr_set = false;
-  auto kern = attn_tc_kernel<DPAD, POLY>;
+  auto kern = attn_tc_kernel<DPAD>;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::Cfg<DPAD>::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(attn_tc): ") + cudaGetErrorString(e));
     attr_set = true;
   }
   dim3 grid((p.Lq + atc::BM - 1) / atc::BM, p.heads, B);
-  launch_k(kern, grid, dim3(320), atc::SMEM_BYTES, st, 1, tq, tk, tv, p);
+  launch_k(kern, grid, dim3(320), atc::Cfg<DPAD>::SMEM_BYTES, st, 1, tq, tk, tv, p);
   count_launch();
   return check_launch("attention_tc launch");
 }
 
-template <int DPAD>
-static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p, int B, cudaStream_t st) {
-  switch (g_attn_poly) {
-    case 2: return launch_attn_tc2<DPAD, 2>(tq, tk, tv, p, B, st);
-    case 4: return launch_attn_tc2<DPAD, 4>(tq, tk, tv, p, B, st);
-    default: return launch_attn_tc2<DPAD, 0>(tq, tk, tv, p, B, st);
-  }
-}
-
 // Returns 1 if this path does not apply (caller falls back to the mma.sync kernel), 0 on success, -1 on error.
 int attention_tc(const GlgAttnArgs* a, cudaStream_t st) {
-  if (a->d_head > 64) return 1;
+  if (a->d_head > 128) return 1;
   // tensor-map constraints: 16-byte aligned bases and strides; the output is written with 16-byte stores
   if ((a->d_head % 8) || (a->o_row % 8) || (a->o_batch % 8) || ((uintptr_t)a->out & 15)) return 1;
   CUtensorMap tq, tk, tv;
@@ -328,10 +320,14 @@ int attention_tc(const GlgAttnArgs* a, cudaStream_t st) {
     case 32: return launch_attn_tc<32>(tq, tk, tv, p, a->B, st);
     case 48: return launch_attn_tc<48>(tq, tk, tv, p, a->B, st);
     case 64: return launch_attn_tc<64>(tq, tk, tv, p, a->B, st);
+    case 80: return launch_attn_tc<80>(tq, tk, tv, p, a->B, st);
+    case 96: return launch_attn_tc<96>(tq, tk, tv, p, a->B, st);
+    case 112: return launch_attn_tc<112>(tq, tk, tv, p, a->B, st);
+    case 128: return launch_attn_tc<128>(tq, tk, tv, p, a->B, st);
   }
   return 1;
 }
 
 }  // namespace glg
 
-extern "C" void glg_debug_attn_poly(int k) { glg::g_attn_poly = k; }
+extern "C" void glg_debug_attn_poly(int) {}   // kept for ABI stability of the test hooks: the FMA-pipe exp2 variants measured slower and were removed

@@ -133,11 +133,11 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
   return d;
 }
 // MN-major operand (e.g. V[key][d] used as B[K=key][N=d]): rows of 64 bf16 along MN (128 B), one row per K
-// index, 8-row groups 1024 B apart (SBO); a single 64-wide MN atom (LBO unused).
-__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr) {
+// index, 8-row groups 1024 B apart (SBO); further 64-wide MN atoms follow at LBO bytes.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes = 16) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;    // LBO: byte offset between 64-element MN atoms
   d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;

@@ -49,11 +49,10 @@ for (d, T, G, heads) in ((40, 4096, 30, 8), (80, 1024, 30, 8), (160, 256, 30, 8)
     qkv = rnd(Bt, T + G, 3 * C)
     out = torch.empty(Bt, T, C, device=dev, dtype=torch.bfloat16)
     kv = rnd(Bt, 77, 2 * C)
-    for mode, mname, poly in ((0, "tc poly/4", 4), (0, "tc poly/2", 2), (0, "tc mufu", 0), (1, "mma_sync", 0)):
-        if d > 64 and mname != "tc poly/4":
+    for mode, mname in ((0, "auto"), (1, "mma_sync")):
+        if d > 128 and mode == 1:
             continue
         ops.lib.glg_debug_attn_mode(mode)
-        ops.lib.glg_debug_attn_poly(poly)
         timeit(f"attn self  d={d} T={T} [{mname}]", lambda: ops.attention(qkv[:, :T, :C], qkv[:, :T, C:2 * C], qkv[:, :T, 2 * C:], out, heads, d),
                flops=4.0 * Bt * heads * T * T * d)
         timeit(f"attn fuser d={d} T={T}+{G} [{mname}]", lambda: ops.attention(qkv[:, :T, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], out, heads, d),
@@ -61,7 +60,6 @@ for (d, T, G, heads) in ((40, 4096, 30, 8), (80, 1024, 30, 8), (160, 256, 30, 8)
         timeit(f"attn cross d={d} T={T}x77 [{mname}]", lambda: ops.attention(out, kv[:, :, :C], kv[:, :, C:], qkv[:, :T, :C].contiguous(), heads, d),
                flops=4.0 * Bt * heads * T * 77 * d)
     ops.lib.glg_debug_attn_mode(0)
-    ops.lib.glg_debug_attn_poly(4)
 
 # ---------------- GEMMs (token GEMMs of the transformer blocks) ----------------
 for cta2, cname in ((1, "1cta"), (2, "2cta"), (0, "auto")):

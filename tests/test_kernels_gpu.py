@@ -233,14 +233,18 @@ ATTN_CASES = [
     (1, 2, 40, 128, 64, "plain"),
     (1, 2, 40, 128, 8192, "plain"),
     (8, 8, 40, 4096, 4126, "fuser"),
+    (2, 8, 80, 1024, 1024, "qkv"),
+    (1, 4, 96, 300, 555, "plain"),
+    (1, 4, 128, 256, 200, "plain"),
+    (1, 4, 72, 128, 130, "plain"),
 ]
 
 
 @pytest.mark.parametrize("B,heads,d,Lq,Lk,mode", ATTN_CASES)
 @pytest.mark.parametrize("path", ["auto", "mma_sync"])
 def test_attention(ops, ref, B, heads, d, Lq, Lk, mode, path):
-    """path=auto: tcgen05/TMEM kernel for d_head <= 64, mma.sync kernel above; path=mma_sync forces the latter."""
-    if path == "mma_sync" and d > 64:
+    """path=auto: tcgen05/TMEM kernel for d_head <= 128, mma.sync kernel above; path=mma_sync forces the latter."""
+    if path == "mma_sync" and d > 128:
         pytest.skip("same kernel as auto")
     C = heads * d
     if mode == "qkv":
