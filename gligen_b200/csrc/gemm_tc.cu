@@ -621,7 +621,7 @@ static void pick_tile(int M, int N, int num_kb, bool geglu, bool conv, int max_s
       const float l2 = 3.05f * (pair ? 128.0f + 0.5f * bn : 128.0f + bn);
       const float per_kb = mma > l2 ? mma : l2;
       for (int sp = 1; sp <= (pair ? 1 : max_splits); ++sp) {
-        if (sp > 1 && (num_kb / sp < 4 || (long long)sp * M * N * 4 > ws_bytes)) break;
+        if (sp > 1 && (num_kb / sp < (g_splitk_mode == 2 ? 4 : 16) || (long long)sp * M * N * 4 > ws_bytes)) break;
         if (sp > 1 && tiles * 2 > units && g_splitk_mode != 2) break;        // only when the tile grid leaves >= half the SMs idle
         if (g_splitk_mode == 2 && max_splits > 1 && sp == 1 && num_kb >= 8) continue;      // test hook: force a split
         const int waves = (tiles * sp + units - 1) / units;
