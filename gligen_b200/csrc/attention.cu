@@ -76,21 +76,25 @@ __device__ __forceinline__ void load_tile(uint32_t smem_tile, const bf16* g, lon
   }
 }
 
-template <int DPAD>
+template <int DPAD, bool SHORT>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnKParams p) {
+  // SHORT (Lk <= 128, the 77-token text context of cross attention): K and V (<= 2 tiles) are loaded ONCE and the
+  // CTA walks QT = 4 consecutive 64-row query tiles with a double-buffered Q, instead of one CTA (and one K/V
+  // fetch, one launch-latency chain) per 64 query rows.
   pdl_trigger();
   pdl_wait();
   using Cfg = AttnCfg<DPAD>;
   constexpr int LDS = Cfg::LDS;
   constexpr int KSTEPS = DPAD / 16;       // k-steps of QK^T
   constexpr int DT = DPAD / 8;            // n-tiles of the output
+  constexpr int NQ = SHORT ? 2 : 1;       // Q buffers
+  constexpr int QT = SHORT ? 4 : 1;       // query tiles per CTA
   extern __shared__ __align__(16) uint8_t attn_smem[];
-  const uint32_t sQ = smem_u32(attn_smem);
-  const uint32_t sK = sQ + Cfg::TILE_ELEMS * 2;
+  const uint32_t sQ0 = smem_u32(attn_smem);
+  const uint32_t sK = sQ0 + NQ * Cfg::TILE_ELEMS * 2;
   const uint32_t sV = sK + 2 * Cfg::TILE_ELEMS * 2;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 64;
   const int h = blockIdx.y, b = blockIdx.z;
   const int d = p.d;
   const bf16* gq = p.q + (long long)b * p.q_batch + (long long)h * d;
@@ -100,22 +104,31 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnKParams p) {
   // zero the padded columns [d, DPAD) of every tile once (cp.async never writes them)
   if (d < DPAD) {
     const int padc = DPAD - d;                   // multiple of 8
-    for (int i = threadIdx.x; i < 5 * 64 * (padc / 8); i += 128) {
+    for (int i = threadIdx.x; i < (4 + NQ) * 64 * (padc / 8); i += 128) {
       const int row = i / (padc / 8), c = i - row * (padc / 8);
       *reinterpret_cast<uint4*>(attn_smem + ((size_t)row * LDS + d + c * 8) * 2) = make_uint4(0, 0, 0, 0);
     }
   }
   const int nkt = (p.Lk + 63) / 64;
-  load_tile<DPAD>(sQ, gq, p.q_row, q0, p.Lq, d);
+  const int qbase = blockIdx.x * 64 * QT;
+  load_tile<DPAD>(sQ0, gq, p.q_row, qbase, p.Lq, d);
   load_tile<DPAD>(sK, gk, p.k_row, 0, p.Lk, d);
   load_tile<DPAD>(sV, gv, p.v_row, 0, p.Lk, d);
+  if (SHORT && nkt > 1) {
+    load_tile<DPAD>(sK + Cfg::TILE_ELEMS * 2, gk, p.k_row, 64, p.Lk, d);
+    load_tile<DPAD>(sV + Cfg::TILE_ELEMS * 2, gv, p.v_row, 64, p.Lk, d);
+  }
   cp_async_commit();
 
   float o_acc[DT][4];
+  float m_run[2], l_run[2];
+  auto reset_state = [&]() {
 #pragma unroll
-  for (int j = 0; j < DT; ++j) { o_acc[j][0] = o_acc[j][1] = o_acc[j][2] = o_acc[j][3] = 0.f; }
-  float m_run[2] = {-INFINITY, -INFINITY};
-  float l_run[2] = {0.f, 0.f};
+    for (int j = 0; j < DT; ++j) { o_acc[j][0] = o_acc[j][1] = o_acc[j][2] = o_acc[j][3] = 0.f; }
+    m_run[0] = m_run[1] = -INFINITY;
+    l_run[0] = l_run[1] = 0.f;
+  };
+  reset_state();
 
   const uint32_t q_lane_off = (uint32_t)((warp * 16 + (lane & 15)) * LDS + (lane >> 4) * 8) * 2u;
   // K (non-transposed) ldmatrix lane offsets: matrix m = lane/8 -> key += (m/2)*8, col += (m%2)*8
@@ -123,20 +136,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnKParams p) {
   // V (transposed) ldmatrix lane offsets: matrix m = lane/8 -> key += (m%2)*8, dcol += (m/2)*8
   const uint32_t v_lane_off = (uint32_t)(((((lane >> 3) & 1) * 8) + (lane & 7)) * LDS + (lane >> 4) * 8) * 2u;
 
-  for (int kt = 0; kt < nkt; ++kt) {
-    const int buf = kt & 1;
-    if (kt + 1 < nkt) {
-      load_tile<DPAD>(sK + (buf ^ 1) * Cfg::TILE_ELEMS * 2, gk, p.k_row, (kt + 1) * 64, p.Lk, d);
-      load_tile<DPAD>(sV + (buf ^ 1) * Cfg::TILE_ELEMS * 2, gv, p.v_row, (kt + 1) * 64, p.Lk, d);
-      cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    const uint32_t sKb = sK + buf * Cfg::TILE_ELEMS * 2;
-    const uint32_t sVb = sV + buf * Cfg::TILE_ELEMS * 2;
-
+  // one 64-key tile: S = Q K^T, mask, online softmax, O += P V
+  auto compute_tile = [&](uint32_t sQ, uint32_t sKb, uint32_t sVb, int kt) {
     // ---- S = Q K^T  (16 x 64 per warp)
     float s[8][4];
 #pragma unroll
@@ -213,10 +214,9 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnKParams p) {
         mma_bf16_16816(o_acc[2 * jp + 1], a0, a1, a2, a3, b2, b3);
       }
     }
-    __syncthreads();
-  }
-
-  // ---- finalise: O /= l, write bf16
+  };
+  // O /= l, write bf16 rows [q0, q0 + 64)
+  auto finalize = [&](int q0) {
   float l0 = l_run[0], l1 = l_run[1];
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
@@ -231,29 +231,73 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnKParams p) {
       if (r1 < p.Lq) *reinterpret_cast<uint32_t*>(go + (long long)r1 * p.o_row + col) = pack_bf16x2(o_acc[j][2] * inv1, o_acc[j][3] * inv1);
     }
   }
+  };
+
+  if constexpr (!SHORT) {
+    for (int kt = 0; kt < nkt; ++kt) {
+      const int buf = kt & 1;
+      if (kt + 1 < nkt) {
+        load_tile<DPAD>(sK + (buf ^ 1) * Cfg::TILE_ELEMS * 2, gk, p.k_row, (kt + 1) * 64, p.Lk, d);
+        load_tile<DPAD>(sV + (buf ^ 1) * Cfg::TILE_ELEMS * 2, gv, p.v_row, (kt + 1) * 64, p.Lk, d);
+        cp_async_commit();
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      compute_tile(sQ0, sK + buf * Cfg::TILE_ELEMS * 2, sV + buf * Cfg::TILE_ELEMS * 2, kt);
+      __syncthreads();
+    }
+    finalize(qbase);
+  } else {
+    for (int s = 0; s < QT; ++s) {
+      const int q0 = qbase + s * 64;
+      if (q0 >= p.Lq) break;
+      const bool more = (s + 1 < QT) && (q0 + 64 < p.Lq);
+      if (more) {
+        load_tile<DPAD>(sQ0 + ((s + 1) & 1) * Cfg::TILE_ELEMS * 2, gq, p.q_row, q0 + 64, p.Lq, d);
+        cp_async_commit();
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      reset_state();
+      for (int kt = 0; kt < nkt; ++kt)
+        compute_tile(sQ0 + (s & 1) * Cfg::TILE_ELEMS * 2, sK + kt * Cfg::TILE_ELEMS * 2, sV + kt * Cfg::TILE_ELEMS * 2, kt);
+      finalize(q0);
+      __syncthreads();            // this Q buffer is refilled two iterations later
+    }
+  }
 }
 
-template <int DPAD>
-static int launch_attn(const AttnKParams& p, int B, cudaStream_t st) {
+template <int DPAD, bool SHORT>
+static int launch_attn2(const AttnKParams& p, int B, cudaStream_t st) {
   using Cfg = AttnCfg<DPAD>;
   static bool attr_set = false;
-  auto kern = attn_fwd_kernel<DPAD>;
+  auto kern = attn_fwd_kernel<DPAD, SHORT>;
+  constexpr int smem = (SHORT ? 6 : 5) * Cfg::TILE_ELEMS * 2;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(attn): ") + cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid((p.Lq + 63) / 64, p.heads, B);
-  launch_k(kern, dim3(grid), dim3(128), Cfg::SMEM_BYTES, st, 1, p);
+  const int rows_per_cta = SHORT ? 256 : 64;
+  dim3 grid((p.Lq + rows_per_cta - 1) / rows_per_cta, p.heads, B);
+  launch_k(kern, dim3(grid), dim3(128), smem, st, 1, p);
   count_launch();
   return check_launch("attention launch");
+}
+template <int DPAD>
+static int launch_attn(const AttnKParams& p, int B, cudaStream_t st) {
+  return p.Lk <= 128 ? launch_attn2<DPAD, true>(p, B, st) : launch_attn2<DPAD, false>(p, B, st);
 }
 
 }  // namespace glg
 
 namespace glg {
 int attention_tc(const GlgAttnArgs* a, cudaStream_t st);   // attention_tc.cu: tcgen05 path for d_head <= 64
-int g_attn_mode = 0;                                       // 0 = auto, 1 = force the mma.sync kernel (test hook)
+int g_attn_mode = 0;          // 0 = auto, 1 = force the mma.sync kernel, 2 = force tcgen05 where it applies (test hooks)
 }
 
 using namespace glg;
@@ -267,7 +311,7 @@ extern "C" int glg_attention(const GlgAttnArgs* a, void* stream) {
   if ((a->q_row | a->k_row | a->v_row | a->q_batch | a->k_batch | a->v_batch) % 8) return set_error("glg_attention: q/k/v strides must be multiples of 8 elements");
   if ((a->o_row | a->o_batch) % 2) return set_error("glg_attention: output strides must be even");
   if (((uintptr_t)a->q | (uintptr_t)a->k | (uintptr_t)a->v) & 15) return set_error("glg_attention: q/k/v must be 16-byte aligned");
-  if (g_attn_mode == 0) {
+  if ((g_attn_mode == 0 && a->Lk > 128) || g_attn_mode == 2) {      // short key sets (text context): the K/V-resident mma.sync kernel below
     const int rc = attention_tc(a, reinterpret_cast<cudaStream_t>(stream));
     if (rc <= 0) return rc;          // 0 = launched, -1 = error; 1 = not applicable -> mma.sync kernel below
   }

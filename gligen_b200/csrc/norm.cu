@@ -43,10 +43,10 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float
                                 int B, int HW, int C, int groups, int rows_per_chunk) {
   pdl_trigger();
   pdl_wait();
-  extern __shared__ float gn_sm[];          // [2][C]
+  extern __shared__ float gn_sm[];          // [2][max(C, 512)]
   __shared__ bool is_last;
   float* s_sum = gn_sm;
-  float* s_sq = gn_sm + C;
+  float* s_sq = gn_sm + (C > 512 ? C : 512);
   const int vec = C >> 3;
   const int rpi = blockDim.x / vec;
   const int cv = threadIdx.x % vec, rl = threadIdx.x / vec;
@@ -103,12 +103,26 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float
   __syncthreads();
   if (is_last) {
     __threadfence();
+    // last CTA of this sample: reduce the per-chunk partials.  Fixed order (deterministic) but spread over the whole
+    // block: thread (g, part) sums chunks part, part + P, ... ; then the P partial sums are added in order.
     const float* pb = scratch + 64 + (long long)B * groups * 2 + (long long)b * chunks * groups * 2;
-    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-      float s = 0.f, ss = 0.f;
-      for (int k = 0; k < chunks; ++k) { s += __ldcg(pb + (long long)k * groups * 2 + g * 2); ss += __ldcg(pb + (long long)k * groups * 2 + g * 2 + 1); }
-      fin[g * 2] = s;
-      fin[g * 2 + 1] = ss;
+    const int P = blockDim.x / groups;                 // groups = 32: P = 7..10 row lanes
+    const int g = threadIdx.x % groups, part = threadIdx.x / groups;
+    float s = 0.f, ss = 0.f;
+    if (part < P) {
+      for (int k = part; k < chunks; k += P) {
+        const float2 t = __ldcg(reinterpret_cast<const float2*>(pb + ((long long)k * groups + g) * 2));
+        s += t.x; ss += t.y;
+      }
+      s_sum[part * groups + g] = s;                    // P * groups <= blockDim <= 512 floats per half
+      s_sq[part * groups + g] = ss;
+    }
+    __syncthreads();
+    if (threadIdx.x < groups) {
+      float ts = 0.f, tss = 0.f;
+      for (int i = 0; i < P; ++i) { ts += s_sum[i * groups + threadIdx.x]; tss += s_sq[i * groups + threadIdx.x]; }
+      fin[threadIdx.x * 2] = ts;
+      fin[threadIdx.x * 2 + 1] = tss;
     }
     if (threadIdx.x == 0) *ticket = 0u;       // ready for the next GroupNorm on this scratch (stream-ordered)
   }
@@ -297,7 +311,7 @@ extern "C" int glg_groupnorm(const void* x, int64_t ldx, void* y, int64_t ldy, c
   dim3 grid(chunks, B);
   if (B > 64) return set_error("glg_groupnorm: at most 64 samples per call");
   if (64 + (long long)B * groups * 2 * (1 + chunks) > (long long)GLG_GN_SCRATCH_FLOATS(B, groups)) return set_error("glg_groupnorm: internal scratch sizing");
-  launch_k(gn_stats_kernel, dim3(grid), dim3(threads), 2 * C * sizeof(float), st, 1, (const bf16*)x, ldx, stats, B, HW, C, groups, rows_per_chunk);
+  launch_k(gn_stats_kernel, dim3(grid), dim3(threads), 2 * (C > 512 ? C : 512) * sizeof(float), st, 1, (const bf16*)x, ldx, stats, B, HW, C, groups, rows_per_chunk);
   count_launch();
   if (check_launch("gn_stats launch")) return -1;
   launch_k(gn_apply_kernel, dim3(grid), dim3(threads), 0, st, 1, (const bf16*)x, ldx, (bf16*)y, ldy, gamma, beta, stats, HW, C, groups, eps, silu, rows_per_chunk);

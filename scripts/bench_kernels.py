@@ -49,8 +49,8 @@ for (d, T, G, heads) in ((40, 4096, 30, 8), (80, 1024, 30, 8), (160, 256, 30, 8)
     qkv = rnd(Bt, T + G, 3 * C)
     out = torch.empty(Bt, T, C, device=dev, dtype=torch.bfloat16)
     kv = rnd(Bt, 77, 2 * C)
-    for mode, mname in ((0, "auto"), (1, "mma_sync")):
-        if d > 128 and mode == 1:
+    for mode, mname in ((0, "auto"), (1, "mma_sync"), (2, "tcgen05")):
+        if d > 128 and mode != 0:
             continue
         ops.lib.glg_debug_attn_mode(mode)
         timeit(f"attn self  d={d} T={T} [{mname}]", lambda: ops.attention(qkv[:, :T, :C], qkv[:, :T, C:2 * C], qkv[:, :T, 2 * C:], out, heads, d),

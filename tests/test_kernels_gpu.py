@@ -237,14 +237,20 @@ ATTN_CASES = [
     (1, 4, 96, 300, 555, "plain"),
     (1, 4, 128, 256, 200, "plain"),
     (1, 4, 72, 128, 130, "plain"),
+    (2, 8, 40, 1000, 128, "kv"),          # short-key kernel: ragged last query tile of a 4-tile CTA, two full K tiles
+    (2, 8, 80, 257, 1, "kv"),
+    (1, 8, 160, 320, 65, "kv"),
 ]
 
 
 @pytest.mark.parametrize("B,heads,d,Lq,Lk,mode", ATTN_CASES)
-@pytest.mark.parametrize("path", ["auto", "mma_sync"])
+@pytest.mark.parametrize("path", ["auto", "mma_sync", "tcgen05"])
 def test_attention(ops, ref, B, heads, d, Lq, Lk, mode, path):
-    """path=auto: tcgen05/TMEM kernel for d_head <= 128, mma.sync kernel above; path=mma_sync forces the latter."""
-    if path == "mma_sync" and d > 128:
+    """path=auto: tcgen05/TMEM kernel for d_head <= 128 and > 128 keys, the K/V-resident mma.sync kernel for short key
+    sets (text context), the streaming mma.sync kernel for d_head > 128; the other two values force one kernel."""
+    if path != "auto" and d > 128:
+        pytest.skip("same kernel as auto")
+    if path == "tcgen05" and Lk > 128:
         pytest.skip("same kernel as auto")
     C = heads * d
     if mode == "qkv":
@@ -261,7 +267,7 @@ def test_attention(ops, ref, B, heads, d, Lq, Lk, mode, path):
         q, k, v = rnd(B, Lq, C), rnd(B, Lk, C, seed=1), rnd(B, Lk, C, seed=2)
     out = torch.zeros(B, Lq, C, device="cuda:0", dtype=torch.bfloat16)
     out_r = torch.zeros_like(out)
-    ops.lib.glg_debug_attn_mode(1 if path == "mma_sync" else 0)
+    ops.lib.glg_debug_attn_mode({"auto": 0, "mma_sync": 1, "tcgen05": 2}[path])
     try:
         ops.attention(q, k, v, out, heads, d)
         torch.cuda.synchronize()
