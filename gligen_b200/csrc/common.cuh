@@ -59,7 +59,10 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = globaltimer_ns();
-  while (!mbar_try_wait(bar, parity)) {
+  while (true) {
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i)          // the timer read is slow: keep it off the wake-up path
+      if (mbar_try_wait(bar, parity)) return;
     if (globaltimer_ns() - t0 > 4000000000ull) {  // 4 s
       printf("glg: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();

@@ -247,10 +247,11 @@ ATTN_CASES = [
 @pytest.mark.parametrize("path", ["auto", "mma_sync", "tcgen05"])
 def test_attention(ops, ref, B, heads, d, Lq, Lk, mode, path):
     """path=auto: tcgen05/TMEM kernel for d_head <= 128 and > 128 keys, the K/V-resident mma.sync kernel for short key
-    sets (text context), the streaming mma.sync kernel for d_head > 128; the other two values force one kernel."""
+    sets (text context), the streaming mma.sync kernel for d_head > 128 (auto picks the one-thread-per-row tcgen05
+    kernel for d_head <= 64 and the row-pair one above); the other two values force mma.sync / the row-pair kernel."""
     if path != "auto" and d > 128:
         pytest.skip("same kernel as auto")
-    if path == "tcgen05" and Lk > 128:
+    if path == "tcgen05" and Lk > 128 and d > 64:
         pytest.skip("same kernel as auto")
     C = heads * d
     if mode == "qkv":
@@ -268,11 +269,13 @@ def test_attention(ops, ref, B, heads, d, Lq, Lk, mode, path):
     out = torch.zeros(B, Lq, C, device="cuda:0", dtype=torch.bfloat16)
     out_r = torch.zeros_like(out)
     ops.lib.glg_debug_attn_mode({"auto": 0, "mma_sync": 1, "tcgen05": 2}[path])
+    ops.lib.glg_debug_attn_tc_variant(1 if path == "tcgen05" else 0)     # 1: the row-pair kernel also for d_head <= 64
     try:
         ops.attention(q, k, v, out, heads, d)
         torch.cuda.synchronize()
     finally:
         ops.lib.glg_debug_attn_mode(0)
+        ops.lib.glg_debug_attn_tc_variant(0)
     ref.attention(q, k, v, out_r, heads, d)
     assert_close(out, out_r, rel=1e-2, max_rel=5e-2, what=f"attention d={d} {Lq}x{Lk} {mode}")
 
