@@ -3,18 +3,21 @@
 // swizzle atoms per operand tile.
 //
 //   per CTA: one (batch, head, 128-query tile); key/value tiles of 64 keys stream through a TMA ring.
-//   warp 0 lane 0 : TMA producer (Q once, then K_j / V_j tiles; 4-D tensor maps {d, head, row, batch},
-//                   box {64, 1, rows, 1}: columns >= d and rows >= L are zero-filled by TMA)
-//   warp 1 lane 0 : MMA issuer   S_j = Q K_j^T          (SS: both operands K-major in smem, N = 64)
-//                                O  += P_j V_j           (TS: P_j bf16 in TMEM, V_j MN-major in smem)
-//   warps 2..9    : softmax      two threads per query row (32 of the tile's 64 keys each; partial row maxima
-//                                are exchanged through smem): tcgen05.ld S_j -> running max (lazy rescale of
-//                                O only when the max grows by > 2^8) -> exp2 -> P_j bf16 -> tcgen05.st.
-//                                8 warps x 2 resident CTAs = 4 softmax warps per SM sub-partition, so TMEM
-//                                reads (64 B/clk/SM) and exp2 (16/clk/SM) - equal cost per score - overlap.
-//   TMEM (256 columns): S[2] (2 x 64 fp32; P_j, 32 packed-bf16 columns, overwrites the first half of S_j once both
-//   warps of a row pair hold their scores in registers) | O (<= 128 fp32).  S is double buffered so QK^T of tile
-//   j+1 overlaps the softmax of tile j; two CTAs are resident per SM.
+//   warp 0 : TMA producer (Q once, then K_j / V_j tiles; 4-D tensor maps {d, head, row, batch},
+//            box {64, 1, rows, 1}: columns >= d and rows >= L are zero-filled by TMA)
+//   warp 1 : MMA issuer   S_j = Q K_j^T          (SS: both operands K-major in smem, N = 64)
+//                         O  += P_j V_j           (TS: P_j bf16 in TMEM, V_j MN-major in smem)
+//            Both run the whole warp through their loops with one elect.sync leader issuing (common.cuh elect_one()).
+//   warps 2..9 : softmax  two threads per query row (32 of the tile's 64 keys each; partial row maxima are
+//            exchanged through smem): tcgen05.ld S_j -> running max (lazy rescale of O only when the max grows by
+//            > 2^8; only that rare path waits for P.V) -> exp2 -> P_j bf16 -> tcgen05.st.
+//   TMEM (256 columns): S[NSB] (64 fp32 each; P_j, 32 packed-bf16 columns, overwrites the first half of S_j once both
+//   warps of a row pair hold their scores in registers) | O (<= 128 fp32).  NSB = 3 for d_head <= 64 (QK^T runs two
+//   key tiles ahead), 2 above.  Two CTAs are resident per SM.
+//   When d_head is not a multiple of 16 the spare V column carries 1.0, so the row sums come out of the P.V MMA.
+//
+// Measured on B200 (profiles/r1_attention_pipeline.md): exp2 16/clk/SM, tcgen05.ld ~466 B/clk/SM, so a 128x128 score
+// block costs >= 1024 clk of MUFU against ~400 clk of tensor pipe: the kernel is bound by the softmax warps.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -31,7 +34,7 @@ struct AttnTcParams {
   int heads, d, Lq, Lk;
   float scale_log2;
   long long* probe;      // PROBE instantiation only: per-phase clock stamps of one softmax warp (scripts/micro)
-  int dbg;               // DBG instantiation only: bit flags that knock out one pipeline piece (scripts/micro)
+  int dbg;               // PROBE instantiation only: bit flags that knock out one pipeline piece (scripts/micro)
 };
 
 namespace atc {
@@ -60,7 +63,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
 #define ATTN_STAMP(k) do { if (PROBE && probe_on) { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_)); stamp[k] += t_ - t_prev; t_prev = t_; } } while (0)
 
 #define EX2PAIR(x) ((PROBE && (p.dbg & 1)) ? (x) : ex2_approx(x))
-template <int DPAD, bool PROBE = false>   // head dim rounded up to a multiple of 16 (<= 128)
+#define ATTN_EV(jj, slot) do { if (PROBE && ev_on && (jj) >= 8 && (jj) < 16) { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_)); p.probe[((jj) - 8) * 16 + (slot)] = t_; } } while (0)
+// ONES (d_head < DPAD): the MMA warp writes 1.0 into column d_head of every V tile, so O[:, d_head] accumulates the
+// row sum of the bf16 P the tensor core actually multiplied - the softmax loop then carries no FADD per score and no
+// running sum to rescale.  The softmax warps are issue-bound (profiles/: ~6 instructions per score, 4 warps per
+// sub-partition), so instructions removed from that loop are time removed from the kernel.
+template <int DPAD, bool PROBE = false, bool ONES = false>   // head dim rounded up to a multiple of 16 (<= 128)
 __global__ void __launch_bounds__(320, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
@@ -95,7 +103,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-    for (int i = 0; i < NSB; ++i) { mbar_init(s_full(i), 1); mbar_init(p_full(i), 256); mbar_init(pv_done(i), 1); }
+    for (int i = 0; i < NSB; ++i) { mbar_init(s_full(i), 1); mbar_init(p_full(i), 8); mbar_init(pv_done(i), 1); }
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -112,44 +120,70 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   pdl_wait();
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
-    mbar_arrive_expect_tx(q_full, C::Q_BYTES);
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp walks the loop, one elected lane issues) =====================
+    const bool leader = elect_one();
+    const bool ev_on = PROBE && (p.dbg & 64) && p.probe && leader && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    if (leader) {
+      mbar_arrive_expect_tx(q_full, C::Q_BYTES);
 #pragma unroll
-    for (int a = 0; a < NATOM; ++a) tma_load_4d(sQ + a * QA_BYTES, &tmQ, q_full, 64 * a, h, q0, b);
+      for (int a = 0; a < NATOM; ++a) tma_load_4d(sQ + a * QA_BYTES, &tmQ, q_full, 64 * a, h, q0, b);
+    }
     int stage = 0; uint32_t phase = 0;
     for (int j = 0; j < nkt; ++j) {
       mbar_wait(kv_empty(stage), phase ^ 1u);
-      if (PROBE && (p.dbg & 16)) { mbar_arrive(kv_full(stage)); if (++stage == STAGES) { stage = 0; phase ^= 1u; } continue; }
-      mbar_arrive_expect_tx(kv_full(stage), 2 * C::KV_BYTES);
-      const uint32_t sk = sKV + stage * 2 * C::KV_BYTES, sv = sk + C::KV_BYTES;
+      ATTN_EV(j, 0);
+      if (leader) {
+        if (PROBE && (p.dbg & 16)) {
+          mbar_arrive(kv_full(stage));
+        } else {
+          mbar_arrive_expect_tx(kv_full(stage), 2 * C::KV_BYTES);
+          const uint32_t sk = sKV + stage * 2 * C::KV_BYTES, sv = sk + C::KV_BYTES;
 #pragma unroll
-      for (int a = 0; a < NATOM; ++a) {
-        tma_load_4d(sk + a * KVA_BYTES, &tmK, kv_full(stage), 64 * a, h, j * BN, b);
-        tma_load_4d(sv + a * KVA_BYTES, &tmV, kv_full(stage), 64 * a, h, j * BN, b);
+          for (int a = 0; a < NATOM; ++a) {
+            tma_load_4d(sk + a * KVA_BYTES, &tmK, kv_full(stage), 64 * a, h, j * BN, b);
+            tma_load_4d(sv + a * KVA_BYTES, &tmV, kv_full(stage), 64 * a, h, j * BN, b);
+          }
+        }
       }
       if (++stage == STAGES) { stage = 0; phase ^= 1u; }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====================
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, BN);            // S = Q K^T : N = 64 keys
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, DPAD, true);    // O += P V  : N = DPAD, B (V) is MN-major
+    const bool leader = elect_one();
+    const bool ev_on = PROBE && (p.dbg & 64) && p.probe && leader && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
     mbar_wait(q_full, 0);
     tc_fence_after();
     auto issue_qk = [&](int j) {
       const int stage = j % STAGES;
       mbar_wait(kv_full(stage), (uint32_t)((j / STAGES) & 1));
       tc_fence_after();
+      ATTN_EV(j, 1);
       const uint32_t sk = sKV + stage * 2 * C::KV_BYTES;
-      const uint32_t d_tmem = tmem_base + S_COL + (j % NSB) * BN;
-      if (!(PROBE && (p.dbg & 2)))
+      if constexpr (ONES) {     // V_j[key][d_head] = 1 (128-byte swizzled rows: 16-byte chunk index ^ (row & 7))
+        const uint32_t svt = sk + C::KV_BYTES;
 #pragma unroll
-      for (int kk = 0; kk < DPAD / 16; ++kk) {        // 16 head-dim columns per step: atom kk/4, +32 B inside the atom
-        const uint64_t qd = umma_desc_kmajor_sw128(sQ + (kk >> 2) * QA_BYTES) + 2 * (kk & 3);
-        const uint64_t kd = umma_desc_kmajor_sw128(sk + (kk >> 2) * KVA_BYTES) + 2 * (kk & 3);
-        umma_bf16(d_tmem, qd, kd, idesc_s, kk != 0 ? 1u : 0u);
+        for (int r = lane; r < BN; r += 32) {
+          const uint32_t a = svt + (uint32_t)r * 128u + ((((uint32_t)p.d >> 3) ^ ((uint32_t)r & 7u)) << 4);
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)0x3F80) : "memory");
+        }
+        fence_proxy_async();    // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        __syncwarp();
       }
-      umma_commit(s_full(j % NSB));
+      const uint32_t d_tmem = tmem_base + S_COL + (j % NSB) * BN;
+      if (leader) {
+        if (!(PROBE && (p.dbg & 2)))
+#pragma unroll
+        for (int kk = 0; kk < DPAD / 16; ++kk) {        // 16 head-dim columns per step: atom kk/4, +32 B inside the atom
+          const uint64_t qd = umma_desc_kmajor_sw128(sQ + (kk >> 2) * QA_BYTES) + 2 * (kk & 3);
+          const uint64_t kd = umma_desc_kmajor_sw128(sk + (kk >> 2) * KVA_BYTES) + 2 * (kk & 3);
+          umma_bf16(d_tmem, qd, kd, idesc_s, kk != 0 ? 1u : 0u);
+        }
+        umma_commit(s_full(j % NSB));
+      }
+      ATTN_EV(j, 2);
     };
     for (int j = 0; j < NSB - 1 && j < nkt; ++j) issue_qk(j);
     for (int j = 0; j < nkt; ++j) {
@@ -157,17 +191,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int stage = j % STAGES, bsel = j % NSB;
       mbar_wait(p_full(bsel), (uint32_t)((j / NSB) & 1));
       tc_fence_after();
+      ATTN_EV(j, 3);
       // V tile: [64 keys][DPAD cols] as NATOM atoms of 64 columns, KVA_BYTES apart (LBO); MN-major B operand
       const uint64_t vdesc = umma_desc_mnmajor_sw128(sKV + stage * 2 * C::KV_BYTES + C::KV_BYTES, KVA_BYTES);
       const uint32_t a_tmem = tmem_base + S_COL + bsel * BN;           // P_j aliases the first 32 columns of S_j
-      if (!(PROBE && (p.dbg & 4)))
+      if (leader) {
+        if (!(PROBE && (p.dbg & 4)))
 #pragma unroll
-      for (int k = 0; k < BN / 16; ++k)           // 16 keys per step: +8 TMEM columns of P, +16 rows (2048 B) of V
-        umma_bf16_ts(tmem_base + O_COL, a_tmem + 8 * k, vdesc + 128 * k, idesc_o, (j | k) != 0 ? 1u : 0u);
-      umma_commit(kv_empty(stage));
-      umma_commit(pv_done(bsel));
+        for (int k = 0; k < BN / 16; ++k)           // 16 keys per step: +8 TMEM columns of P, +16 rows (2048 B) of V
+          umma_bf16_ts(tmem_base + O_COL, a_tmem + 8 * k, vdesc + 128 * k, idesc_o, (j | k) != 0 ? 1u : 0u);
+        umma_commit(kv_empty(stage));
+        umma_commit(pv_done(bsel));
+      }
+      ATTN_EV(j, 4);
     }
-    umma_commit(o_full);
+    if (leader) umma_commit(o_full);
   } else if (warp >= 2) {
     // ===================== softmax / correction / output =====================
     const int q = warp & 3;                      // TMEM lane quarter
@@ -180,18 +218,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
     float m_ref = -INFINITY;        // reference max (raw score units) the stored P / O are relative to
     float l = 0.f;                  // this thread's partial row sum (its 32 keys per tile)
-    long long stamp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_prev = 0;
-    const bool probe_on = PROBE && p.probe != nullptr && lane == 0 && (warp == 2 || warp == 7);
+    long long stamp[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_prev = 0;
+    const bool probe_on = PROBE && !(p.dbg & 64) && p.probe != nullptr && lane == 0 && (warp == 2 || warp == 7);
+    const bool ev_on = PROBE && (p.dbg & 64) && p.probe && lane == 0 && warp == 2 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
     if (PROBE && probe_on) asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_prev));
     for (int j = 0; j < nkt; ++j) {
       const int bsel = j % NSB;
-      mbar_wait(s_full(bsel), (uint32_t)((j / NSB) & 1));
-      tc_fence_after();
       ATTN_STAMP(0);
+      mbar_wait(s_full(bsel), (uint32_t)((j / NSB) & 1));
+      ATTN_STAMP(1);
+      tc_fence_after();
+      ATTN_STAMP(2);
+      ATTN_EV(j, 5);
       uint32_t sv[32];
       tmem_ld32(lane_base + S_COL + bsel * BN + hc * 32, sv);
+      ATTN_STAMP(3);
       tmem_ld_wait();
-      ATTN_STAMP(1);
+      ATTN_STAMP(4);
       if (j == nkt - 1 && (p.Lk & (BN - 1))) {
         const int valid = p.Lk - j * BN - hc * 32;      // keys [valid, 32) of this half are padding
 #pragma unroll
@@ -204,18 +247,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // row max over both column halves: exchange through smem with the partner warp (same rows).  After this
       // barrier BOTH warps hold their scores in registers, so P may overwrite the S columns.
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch_addr(j & 1, hc, rloc)), "f"(mx) : "memory");
+      ATTN_STAMP(5);
       pair_sync();
+      ATTN_STAMP(6);
       float other;
       asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch_addr(j & 1, hc ^ 1, rloc)) : "memory");
       mx = fmaxf(mx, other);
-      ATTN_STAMP(2);
-      ATTN_STAMP(3);
       const float m_new = fmaxf(m_ref, mx);
       if (j == 0) {
         m_ref = m_new;
       } else {
         const bool need = (m_new - m_ref) * sl2 > RESCALE_THRESHOLD;
-        if (__any_sync(0xffffffffu, need)) {     // tcgen05.ld/st are warp-collective: whole warp rescales
+        const bool any_need = __any_sync(0xffffffffu, need);
+        ATTN_STAMP(7);
+        if (any_need) {     // tcgen05.ld/st are warp-collective: whole warp rescales
           // Only the (rare) rescale touches O, so only it waits for PV_{j-1}: the common path never waits on the
           // P.V MMAs, and the softmax warps run back to back while the MMA issuer trails one tile behind.  Skipping
           // waits is phase-safe: PV_{j+1} cannot complete before this thread's p_full(j+1) arrival, so pv_done never
@@ -223,7 +268,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           mbar_wait(pv_done((j - 1) % NSB), (uint32_t)(((j - 1) / NSB) & 1));
           tc_fence_after();
           const float f = need ? ex2_approx((m_ref - m_new) * sl2) : 1.0f;
-          if (need) { m_ref = m_new; l *= f; }
+          if (need) { m_ref = m_new; if constexpr (!ONES) l *= f; }
 #pragma unroll
           for (int c = 0; c < DPAD / 16; ++c) {
             if ((c & 1) != hc) continue;         // the two warps of a lane quarter split the O columns
@@ -237,7 +282,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tmem_st_wait();
         }
       }
-      ATTN_STAMP(4);
+      ATTN_STAMP(8);
       const float ms = m_ref * sl2;
       uint32_t pk[16];
       float sum = 0.f;
@@ -245,30 +290,45 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       for (int i = 0; i < 16; ++i) {
         const float a0 = EX2PAIR(fmaf(__uint_as_float(sv[2 * i]), sl2, -ms));
         const float a1 = EX2PAIR(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -ms));
-        sum += a0 + a1;
+        if constexpr (!ONES) sum += a0 + a1;
         pk[i] = pack_bf16x2(a0, a1);
       }
-      l += sum;
-      ATTN_STAMP(5);
+      if constexpr (!ONES) l += sum;
+      ATTN_STAMP(9);
       tmem_st16(lane_base + S_COL + bsel * BN + hc * 16, pk);
+      ATTN_STAMP(10);
       tmem_st_wait();
+      ATTN_STAMP(11);
       tc_fence_before();
-      mbar_arrive(p_full(bsel));
-      ATTN_STAMP(6);
+      ATTN_STAMP(12);
+      __syncwarp();
+      ATTN_STAMP(13);
+      if (lane == 0) mbar_arrive(p_full(bsel));       // one arrival per warp: 256 same-address arrivals serialise in the smem pipe
+      ATTN_STAMP(14);
+      ATTN_EV(j, 6);
     }
     if (PROBE && probe_on) {
       const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-      long long* dst = p.probe + ((long long)cta * 2 + (warp == 7)) * 8;
-      for (int i = 0; i < 8; ++i) dst[i] = stamp[i];
+      long long* dst = p.probe + ((long long)cta * 2 + (warp == 7)) * 16;
+      for (int i = 0; i < 16; ++i) dst[i] = stamp[i];
     }
     // ---- epilogue: total row sum, O / l -> bf16
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch_addr(nkt & 1, hc, rloc)), "f"(l) : "memory");
-    pair_sync();
-    float l_other;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l_other) : "r"(xch_addr(nkt & 1, hc ^ 1, rloc)) : "memory");
-    mbar_wait(o_full, 0);
-    tc_fence_after();
-    const float inv = 1.0f / (l + l_other);
+    float inv;
+    if constexpr (ONES) {
+      mbar_wait(o_full, 0);
+      tc_fence_after();
+      const uint32_t lsum = tmem_ld1(lane_base + O_COL + p.d);              // column d_head of O = sum_j P_j . 1
+      tmem_ld_wait();
+      inv = 1.0f / __uint_as_float(lsum);
+    } else {
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch_addr(nkt & 1, hc, rloc)), "f"(l) : "memory");
+      pair_sync();
+      float l_other;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(l_other) : "r"(xch_addr(nkt & 1, hc ^ 1, rloc)) : "memory");
+      mbar_wait(o_full, 0);
+      tc_fence_after();
+      inv = 1.0f / (l + l_other);
+    }
     bf16* orow = p.o + (long long)b * p.o_batch + (long long)row * p.o_row + (long long)h * p.d;
 #pragma unroll
     for (int c = 0; c < DPAD / 16; ++c) {
@@ -303,271 +363,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 }
 
 
-// ---------------------------------------------------------------------------------------------------------------
-// Head dims <= 64 (d_head = 40: the 64x64-latent level, 80 % of all attention time).  Per score this kernel costs one
-// exp2, and the SM's 16 exp2/clk is the only hard bound (a 128x64 score tile = 512 clk of MUFU against ~100 clk of
-// tensor pipe), so the design goal is to keep MUFU fed: the phases that are pure latency for one CTA (mbarrier
-// hand-offs, tcgen05.ld round trips, the P store) are hidden behind the exp2 phases of OTHER CTAs.
-//   * 128 TMEM columns per CTA (S 64 fp32, single-buffered; P_j aliases it; O <= 64) -> FOUR resident CTAs per SM,
-//     each with four softmax warps = four independent softmax streams per SM sub-partition;
-//   * one thread per query row (no cross-thread max exchange, no named barriers);  scores are read twice from TMEM
-//     (max pass, exp pass) instead of held in 64 registers, keeping the kernel at <= 80 registers for 4 CTAs/SM;
-//   * two mbarrier hand-offs per key tile: s_full (QK_j and, by commit ordering, PV_{j-1} complete) and p_full.
-namespace atc1 {
-constexpr int BM = 128, BN = 64, STAGES = 2;
-constexpr int Q_BYTES = BM * 64 * 2, KV_BYTES = BN * 64 * 2;
-constexpr int TMEM_COLS = 128, S_COL = 0, O_COL = 64;
-constexpr int SMEM_BYTES = Q_BYTES + STAGES * 2 * KV_BYTES + 1024 + 128;
-}  // namespace atc1
-
-#define S1_STAMP(k) do { if (DBG && probe_on && j >= 8 && j < 16) { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_)); p.probe[(j - 8) * 16 + (k)] = t_; } } while (0)
-#define EX2S1(x) ((DBG && (p.dbg & 1)) ? (x) : ex2_approx(x))
-template <int DPAD, bool DBG = false>   // 16, 32, 48 or 64
-__global__ void __launch_bounds__(192, DBG ? 1 : 4)
-attn_tc_s1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                  const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
-  using namespace atc1;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = base;
-  const uint32_t sKV = base + Q_BYTES;                  // per stage: K | V
-  const uint32_t bar_base = sKV + STAGES * 2 * KV_BYTES;
-  const uint32_t q_full = bar_base;
-  auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
-  auto kv_empty = [&](int s) { return bar_base + 8u * (1 + STAGES + s); };
-  const uint32_t s_full = bar_base + 8u * (1 + 2 * STAGES);
-  const uint32_t p_full = s_full + 8u;
-  const uint32_t o_full = s_full + 16u;
-  const uint32_t tmem_slot = s_full + 24u;
-
-  pdl_trigger();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BM;
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int nkt = (p.Lk + BN - 1) / BN;
-
-  if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) {
-    if (lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
-    __syncwarp();
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  pdl_wait();
-
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
-    mbar_arrive_expect_tx(q_full, Q_BYTES);
-    tma_load_4d(sQ, &tmQ, q_full, 0, h, q0, b);
-    int stage = 0; uint32_t phase = 0;
-    for (int j = 0; j < nkt; ++j) {
-      mbar_wait(kv_empty(stage), phase ^ 1u);
-      if (DBG && (p.dbg & 16)) { mbar_arrive(kv_full(stage)); if (++stage == STAGES) { stage = 0; phase ^= 1u; } continue; }
-      mbar_arrive_expect_tx(kv_full(stage), 2 * KV_BYTES);
-      const uint32_t sk = sKV + stage * 2 * KV_BYTES;
-      tma_load_4d(sk, &tmK, kv_full(stage), 0, h, j * BN, b);
-      tma_load_4d(sk + KV_BYTES, &tmV, kv_full(stage), 0, h, j * BN, b);
-      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-    }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc_s = umma_idesc_bf16(128, BN);
-    constexpr uint32_t idesc_o = umma_idesc_bf16(128, DPAD, true);
-    mbar_wait(q_full, 0);
-    tc_fence_after();
-    const bool probe_on = DBG && p.probe != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-    for (int j = 0; j < nkt; ++j) {
-      const int stage = j % STAGES;
-      mbar_wait(kv_full(stage), (uint32_t)((j / STAGES) & 1));
-      tc_fence_after();
-      S1_STAMP(8);
-      const uint32_t sk = sKV + stage * 2 * KV_BYTES;
-      // S_j = Q K_j^T: issued behind PV_{j-1} on the in-order tensor pipe, so it overwrites P_{j-1} only after use
-      if (!(DBG && (p.dbg & 2)))
-#pragma unroll
-      for (int kk = 0; kk < DPAD / 16; ++kk)
-        umma_bf16(tmem_base + S_COL, umma_desc_kmajor_sw128(sQ) + 2 * kk, umma_desc_kmajor_sw128(sk) + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
-      umma_commit(s_full);                       // also covers PV_{j-1}: O is stable when the softmax warps see S_j
-      S1_STAMP(9);
-      mbar_wait(p_full, (uint32_t)(j & 1));
-      tc_fence_after();
-      S1_STAMP(10);
-      const uint64_t vdesc = umma_desc_mnmajor_sw128(sk + KV_BYTES, KV_BYTES);
-      if (!(DBG && (p.dbg & 4)))
-#pragma unroll
-      for (int k = 0; k < BN / 16; ++k)
-        umma_bf16_ts(tmem_base + O_COL, tmem_base + S_COL + 8 * k, vdesc + 128 * k, idesc_o, (j | k) != 0 ? 1u : 0u);
-      umma_commit(kv_empty(stage));
-      S1_STAMP(11);
-    }
-    umma_commit(o_full);
-  } else if (warp >= 2) {
-    // ===================== softmax / correction / output: one thread per query row =====================
-    const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int row = q0 + q * 32 + lane;
-    const float sl2 = p.scale_log2;
-    const bool ragged = (p.Lk & (BN - 1)) != 0;
-    float m_ref = -INFINITY, l = 0.f;
-    const bool probe_on = DBG && p.probe != nullptr && lane == 0 && warp == 2 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
-    for (int j = 0; j < nkt; ++j) {
-      mbar_wait(s_full, (uint32_t)(j & 1));
-      tc_fence_after();
-      S1_STAMP(0);
-      const bool mask = ragged && j == nkt - 1;
-      const int valid = p.Lk - j * BN;            // keys [valid, 64) of this tile are padding (only if mask)
-      uint32_t sv[32];
-      // ---- pass 1: row max.  Keys 32..63 first (dropped), then keys 0..31 (kept in registers for pass 2).
-      float mx = -INFINITY;
-      tmem_ld32(lane_base + S_COL + 32, sv);
-      tmem_ld_wait();
-      if (mask) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) if (32 + i >= valid) sv[i] = 0xff800000u;
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
-      S1_STAMP(1);
-      tmem_ld32(lane_base + S_COL, sv);
-      tmem_ld_wait();
-      if (mask) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) if (i >= valid) sv[i] = 0xff800000u;
-      }
-#pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
-      S1_STAMP(2);
-      const float m_new = fmaxf(m_ref, mx);
-      if (j == 0) {
-        m_ref = m_new;
-      } else {
-        const bool need = (m_new - m_ref) * sl2 > atc::RESCALE_THRESHOLD;
-        if (__any_sync(0xffffffffu, need)) {     // tcgen05.ld/st are warp-collective: the whole warp rescales
-          const float f = need ? ex2_approx((m_ref - m_new) * sl2) : 1.0f;
-          if (need) { m_ref = m_new; l *= f; }
-#pragma unroll
-          for (int c = 0; c < DPAD / 16; ++c) {
-            uint32_t o[16];
-            tmem_ld16(lane_base + O_COL + c * 16, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-            tmem_st16(lane_base + O_COL + c * 16, o);
-          }
-        }
-      }
-      // ---- pass 2: P = exp2(s * scale - m), bf16, into the first 32 columns of the S buffer
-      S1_STAMP(3);
-      const float ms = m_ref * sl2;
-      float sum = 0.f;
-      uint32_t pk[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float a0 = EX2S1(fmaf(__uint_as_float(sv[2 * i]), sl2, -ms));
-        const float a1 = EX2S1(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -ms));
-        sum += a0 + a1;
-        pk[i] = pack_bf16x2(a0, a1);
-      }
-      S1_STAMP(4);
-      tmem_st16(lane_base + S_COL, pk);              // keys 0..31 -> columns 0..15 (their scores are in registers)
-      tmem_ld32(lane_base + S_COL + 32, sv);         // keys 32..63 again (columns 32..63 are still intact)
-      tmem_ld_wait();
-      if (mask) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) if (32 + i >= valid) sv[i] = 0xff800000u;
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float a0 = EX2S1(fmaf(__uint_as_float(sv[2 * i]), sl2, -ms));
-        const float a1 = EX2S1(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -ms));
-        sum += a0 + a1;
-        pk[i] = pack_bf16x2(a0, a1);
-      }
-      l += sum;
-      S1_STAMP(5);
-      tmem_st16(lane_base + S_COL + 16, pk);         // keys 32..63 -> columns 16..31
-      tmem_st_wait();
-      S1_STAMP(6);
-      tc_fence_before();
-      mbar_arrive(p_full);
-      S1_STAMP(7);
-    }
-
-    // ---- epilogue: O / l -> bf16
-    mbar_wait(o_full, 0);
-    tc_fence_after();
-    const float inv = 1.0f / l;
-    bf16* orow = p.o + (long long)b * p.o_batch + (long long)row * p.o_row + (long long)h * p.d;
-#pragma unroll
-    for (int c = 0; c < DPAD / 16; ++c) {
-      uint32_t o[16];
-      tmem_ld16(lane_base + O_COL + c * 16, o);
-      tmem_ld_wait();
-      if (row < p.Lq) {
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int col = c * 16 + g * 8;
-          if (col < p.d) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
-            u.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
-            u.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
-            u.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
-            *reinterpret_cast<uint4*>(orow + col) = u;
-          }
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    __syncwarp();
-    tc_fence_after();
-    tmem_dealloc(tmem_base, atc1::TMEM_COLS);
-  }
-}
-
-int g_attn_tc_variant = 0;     // 0 = auto, 1 = row-pair kernel for every d_head, 2 = one-thread-per-row kernel where it applies
-
-int g_attn_dbg = 0;
-int g_attn_extra_smem = 0;
-template <int DPAD, bool DBG = false>
-static int launch_attn_tc_s1(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p, int B, cudaStream_t st) {
-  static bool attr_set = false;
-  auto kern = attn_tc_s1_kernel<DPAD, DBG>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, atc1::SMEM_BYTES);
-    if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(attn_tc_s1): ") + cudaGetErrorString(e));
-    attr_set = true;
-  }
-  dim3 grid((p.Lq + atc1::BM - 1) / atc1::BM, p.heads, B);
-  if (g_attn_extra_smem) {     // occupancy experiment (scripts/micro): pad the request so fewer CTAs fit per SM
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, atc1::SMEM_BYTES + g_attn_extra_smem);
-    attr_set = false;
-  }
-  launch_k(kern, grid, dim3(192), atc1::SMEM_BYTES + g_attn_extra_smem, st, 1, tq, tk, tv, p);
-  count_launch();
-  return check_launch("attention_tc_s1 launch");
-}
+int g_attn_tc_variant = 0;     // test hook: 0 = auto, 1 = PROBE build where asked (scripts/micro), 3 = no ones-column row sum
+int g_attn_dbg = 0;            // PROBE build only: knock-out flags (1 MUFU, 2 QK^T MMAs, 4 P.V MMAs, 16 K/V TMA), 64 = event trace
 
 long long* g_attn_probe = nullptr;
 
-template <int DPAD, bool PROBE = false>
+template <int DPAD, bool PROBE = false, bool ONES = false>
 static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p, int B, cudaStream_t st) {
   static bool attr_set = false;
-  auto kern = attn_tc_kernel<DPAD, PROBE>;
+  auto kern = attn_tc_kernel<DPAD, PROBE, ONES>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, atc::Cfg<DPAD>::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(attn_tc): ") + cudaGetErrorString(e));
@@ -607,19 +411,14 @@ int attention_tc(const GlgAttnArgs* a, cudaStream_t st) {
   p.probe = g_attn_probe;
   p.dbg = g_attn_dbg;
   const int dpad = (a->d_head + 15) / 16 * 16;
-  if (dpad <= 64 && g_attn_tc_variant != 1) {
-    switch (dpad) {
-      case 16: return launch_attn_tc_s1<16>(tq, tk, tv, p, a->B, st);
-      case 32: return launch_attn_tc_s1<32>(tq, tk, tv, p, a->B, st);
-      case 48: return (g_attn_dbg || g_attn_probe) ? launch_attn_tc_s1<48, true>(tq, tk, tv, p, a->B, st) : launch_attn_tc_s1<48>(tq, tk, tv, p, a->B, st);
-      case 64: return launch_attn_tc_s1<64>(tq, tk, tv, p, a->B, st);
-    }
-  }
+  const bool ones = a->d_head < dpad && g_attn_tc_variant != 3;      // a spare V column carries the row sum
   switch (dpad) {
-    case 16: return launch_attn_tc<16>(tq, tk, tv, p, a->B, st);
-    case 32: return launch_attn_tc<32>(tq, tk, tv, p, a->B, st);
-    case 48: return ((g_attn_probe || g_attn_dbg) && g_attn_tc_variant == 1) ? launch_attn_tc<48, true>(tq, tk, tv, p, a->B, st) : launch_attn_tc<48>(tq, tk, tv, p, a->B, st);
-    case 64: return launch_attn_tc<64>(tq, tk, tv, p, a->B, st);
+    case 16: return ones ? launch_attn_tc<16, false, true>(tq, tk, tv, p, a->B, st) : launch_attn_tc<16>(tq, tk, tv, p, a->B, st);
+    case 32: return ones ? launch_attn_tc<32, false, true>(tq, tk, tv, p, a->B, st) : launch_attn_tc<32>(tq, tk, tv, p, a->B, st);
+    case 48:
+      if ((g_attn_probe || g_attn_dbg) && g_attn_tc_variant == 1) return launch_attn_tc<48, true>(tq, tk, tv, p, a->B, st);
+      return ones ? launch_attn_tc<48, false, true>(tq, tk, tv, p, a->B, st) : launch_attn_tc<48>(tq, tk, tv, p, a->B, st);
+    case 64: return ones ? launch_attn_tc<64, false, true>(tq, tk, tv, p, a->B, st) : launch_attn_tc<64>(tq, tk, tv, p, a->B, st);
     case 80: return launch_attn_tc<80>(tq, tk, tv, p, a->B, st);
     case 96: return launch_attn_tc<96>(tq, tk, tv, p, a->B, st);
     case 112: return launch_attn_tc<112>(tq, tk, tv, p, a->B, st);
@@ -633,4 +432,4 @@ int attention_tc(const GlgAttnArgs* a, cudaStream_t st) {
 // test hook: device buffer of [ctas][2 warps][8] int64 phase-clock sums for the d_head = 40 kernel (nullptr = off)
 extern "C" void glg_debug_attn_probe(void* buf) { glg::g_attn_probe = reinterpret_cast<long long*>(buf); }
 extern "C" void glg_debug_attn_tc_variant(int v) { glg::g_attn_tc_variant = v; }
-extern "C" void glg_debug_attn_poly(int v) { if (v >= 1024 || v < 0) glg::g_attn_extra_smem = v < 0 ? 0 : v; else glg::g_attn_dbg = v; }   // knock-out flags of the DBG instantiation (scripts/micro)   // kept for ABI stability of the test hooks: the FMA-pipe exp2 variants measured slower and were removed
+extern "C" void glg_debug_attn_poly(int v) { glg::g_attn_dbg = v; }   // knock-out / trace flags of the PROBE instantiation (scripts/micro)

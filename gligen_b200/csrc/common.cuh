@@ -70,6 +70,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// One leader lane of a fully converged warp.  The single-thread roles (TMA producer, MMA issuer) run the whole warp
+// through their loops and predicate the issue on this flag: a role entered as `if (lane == 0)` makes the compiler wrap
+// every UTCHMMA / UTCBAR / UTMALDG in an ELECT + BRA.U.ANY loop over "the active lanes" (~6 slow uniform-datapath
+// instructions each); with elect.sync the same instructions are emitted back to back, predicated.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ TMA (tiled tensor maps)
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
@@ -156,6 +166,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool b_mn_m
        | ((uint32_t)(M >> 4) << 24);    // M / 16
 }
 
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {     // one 32-bit column of this thread's lane
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
+}
 // TMEM -> registers: 32 lanes x 32 columns of 32-bit; thread i of the warp receives lane (base+i).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

@@ -417,8 +417,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int total_work = p.tiles_m * p.tiles_n * p.splits;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     // ===================== TMA producer (every CTA loads its own 128 rows of A and its share of B) ==========
+    // whole warp walks the loop, one elected lane issues (see elect_one())
+    const bool leader = elect_one();
     int stage = 0; uint32_t phase = 0;
     for (int work = unit; work < total_work; work += num_units) {
       const int tile = work / p.splits, split = work - tile * p.splits;
@@ -437,11 +439,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int kb = kb_lo + (int)(((unsigned)tile * 3u) % (unsigned)kb_n);
       for (int it = 0; it < kb_n; ++it, kb = (kb + 1 == kb_lo + kb_n) ? kb_lo : kb + 1) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
-        // the leader's barrier collects the bytes of both CTAs
-        if (!CTA2) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-        else if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
         const uint32_t a_dst = base + stage * Cfg::STAGE_BYTES;
         const uint32_t b_dst = a_dst + Cfg::A_BYTES;
+        if (leader) {
+        // the leader CTA's barrier collects the bytes of both CTAs
+        if (!CTA2) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+        else if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
         if (p.conv) {
           const int tap = kb / p.kb_per_tap;
           const int cb = kb - tap * p.kb_per_tap;
@@ -462,12 +465,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_2d(b_dst, &tmB, full_bar(stage), kb * 64, brow0);
           }
         }
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1 && lane == 0 && rank == 0) {
-    // ===================== MMA issuer (leader CTA only) =====================
+  } else if (warp == 1 && rank == 0) {
+    // ===================== MMA issuer (leader CTA only; one elected lane issues, see elect_one()) =====================
     constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 256 : 128, BN);
+    const bool leader = elect_one();
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int work = unit; work < total_work; work += num_units) {
@@ -482,15 +487,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t a_addr = base + stage * Cfg::STAGE_BYTES;
         const uint64_t adesc = umma_desc_kmajor_sw128(a_addr);
         const uint64_t bdesc = umma_desc_kmajor_sw128(a_addr + Cfg::A_BYTES);
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {   // 4 x K=16 inside one 64-wide (128 B) swizzle atom: +32 B per step
-          if constexpr (CTA2) umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {   // 4 x K=16 inside one 64-wide (128 B) swizzle atom: +32 B per step
+            if constexpr (CTA2) umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if constexpr (CTA2) umma_commit_2sm(empty_bar(stage)); else umma_commit(empty_bar(stage));
         }
-        if constexpr (CTA2) umma_commit_2sm(empty_bar(stage)); else umma_commit(empty_bar(stage));
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      if constexpr (CTA2) umma_commit_2sm(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
+      if (leader) {
+        if constexpr (CTA2) umma_commit_2sm(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
+      }
       if (++acc == ACC) { acc = 0; acc_phase ^= 1u; }
     }
   } else if (warp >= 2) {

@@ -1,71 +1,97 @@
 #!/usr/bin/env python
-"""Phase breakdown of the d_head=40 tcgen05 attention kernel (clock64 stamps of two softmax warps per CTA)."""
-import os, sys
+"""Pipeline probes of the d_head = 40 tcgen05 attention kernel at the L0 shape (8 x 8 heads x 4096 x 4096).
+
+Uses the PROBE instantiation of attn_tc_kernel<48> (test hooks glg_debug_attn_probe / _poly / _tc_variant):
+  * knock-outs: the kernel with MUFU / QK^T MMAs / P.V MMAs / K,V TMA loads removed (results are wrong, time is real)
+  * phase stamps: clock64 deltas accumulated by two softmax warps of every CTA, averaged per key tile
+  * event trace: absolute clock64 of the TMA, MMA and one softmax warp of CTA 0 for key tiles 8..15
+Output of the B200 run is summarised in profiles/r1_attention_pipeline.md.
+"""
+import os
+import sys
+
 import torch
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-from gligen_b200.ops import CudaOps
-dev = "cuda:0"; ops = CudaOps(dev)
+from gligen_b200.ops import CudaOps  # noqa: E402
+
+dev = "cuda:0"
+ops = CudaOps(dev)
 B, heads, d, T = 8, 8, 40, 4096
 C = heads * d
 qkv = (torch.randn(B, T, 3 * C, device=dev)).to(torch.bfloat16)
 out = torch.empty(B, T, C, device=dev, dtype=torch.bfloat16)
-run = lambda: ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], out, heads, d)
+nct = (T // 128) * heads * B
+nkt = T // 64
+
+
+def run():
+    ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], out, heads, d)
+
+
 def timeit(n=10):
-    for _ in range(3): run()
+    for _ in range(3):
+        run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(n): run()
-    e1.record(); torch.cuda.synchronize()
+    for _ in range(n):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n * 1e3
-print(f"s1 kernel: {timeit():.1f} us")
-for kb, nc in ((0, 4), (20, 3), (60, 2), (120, 1)):
-    ops.lib.glg_debug_attn_poly(kb * 1024 if kb else -1)
-    t = timeit()
-    print(f"  s1 with {nc} CTA/SM: {t:.1f} us -> {t * 1e-6 * 1.965e9 * nc * 148 / (2048 * 64):.0f} clk per CTA-iteration")
-ops.lib.glg_debug_attn_poly(-1)
-for flags, nm in ((32, "dbg build, nothing off"), (1, "no MUFU"), (2, "no QK mma"), (4, "no PV mma"), (6, "no mma"), (16, "no K/V TMA"), (7, "no MUFU, no mma"), (23, "no MUFU/mma/TMA")):
-    ops.lib.glg_debug_attn_poly(flags)
-    print(f"  s1 [{nm}]: {timeit():.1f} us")
-ops.lib.glg_debug_attn_poly(0)
+
+
+print(f"production kernel (ones-column row sum): {timeit():.1f} us")
+ops.lib.glg_debug_attn_tc_variant(3)
+print(f"production kernel (softmax-side row sum): {timeit():.1f} us")
 ops.lib.glg_debug_attn_tc_variant(1)
-for flags, nm in ((32, "dbg build, nothing off"), (1, "no MUFU"), (2, "no QK mma"), (4, "no PV mma"), (16, "no K/V TMA"), (17, "no TMA, no MUFU"), (23, "no TMA/MUFU/mma")):
+for flags, nm in ((32, "nothing off"), (1, "no MUFU"), (2, "no QK mma"), (4, "no PV mma"), (16, "no K/V TMA"), (23, "no MUFU/mma/TMA")):
     ops.lib.glg_debug_attn_poly(flags)
-    print(f"  pair [{nm}]: {timeit():.1f} us")
+    print(f"  PROBE build [{nm}]: {timeit():.1f} us")
 ops.lib.glg_debug_attn_poly(0)
-print(f"pair kernel: {timeit():.1f} us")
-ref = out.clone()
-ops.lib.glg_debug_attn_tc_variant(0)
-run(); torch.cuda.synchronize()
-print("max |s1 - pair| =", (out.float() - ref.float()).abs().max().item())
-nct = (T // 128) * heads * B
-nkt = T // 64
-def probe(variant, names, label):
-    buf = torch.zeros(nct * 2 * 8, dtype=torch.int64, device=dev)
-    ops.lib.glg_debug_attn_tc_variant(variant)
+
+PHASES = ["loop top", "mbar_wait s_full", "fence_after", "ld issue", "ld wait", "max+sts", "bar.sync", "lds+vote", "rescale",
+          "exp loop", "st issue", "st wait", "fence_before", "syncwarp", "arrive", "-"]
+
+
+def phases(flags, label):
+    buf = torch.zeros(nct * 2 * 16, dtype=torch.int64, device=dev)
+    ops.lib.glg_debug_attn_poly(flags)
     ops.lib.glg_debug_attn_probe(buf.data_ptr())
-    print(f"{label} probe build: {timeit():.1f} us")
-    buf.zero_(); run(); torch.cuda.synchronize()
+    t = timeit()
+    buf.zero_()
+    run()
+    torch.cuda.synchronize()
     ops.lib.glg_debug_attn_probe(None)
-    ops.lib.glg_debug_attn_tc_variant(0)
-    st = buf.view(nct, 2, 8).double()
+    ops.lib.glg_debug_attn_poly(0)
+    st = buf.view(nct, 2, 16).double()
+    print(f"phase stamps [{label}] ({t:.1f} us with stamps; each stamp costs ~20 clk):")
     for w in range(2):
         m = st[:, w].mean(0) / nkt
-        print(f"  warp {w}: " + "  ".join(f"{n}={v:.0f}" for n, v in zip(names, m.tolist())) + f"  | total/iter={m.sum():.0f} clk")
-probe(1, ["wait s_full", "tmem ld S", "max+exchange", "wait pv_done", "rescale", "exp loop", "st P+arrive", "-"], "pair")
-def trace(extra_kb, label):
-    buf = torch.zeros(8 * 16, dtype=torch.int64, device=dev)
-    ops.lib.glg_debug_attn_poly(extra_kb * 1024 if extra_kb else -1)
-    ops.lib.glg_debug_attn_probe(buf.data_ptr())
-    run(); torch.cuda.synchronize()
-    t = timeit()
-    buf.zero_(); run(); torch.cuda.synchronize()
-    ops.lib.glg_debug_attn_probe(None); ops.lib.glg_debug_attn_poly(-1)
-    ev = buf.view(8, 16).cpu()
-    t0 = int(ev[0, 8])
-    print(f"{label}: {t:.1f} us; event trace of CTA 0 (clk rel. to MMA kv_full wake of iteration 8)")
-    names = {8: "M kv_full ok", 9: "M QK issued+commit", 0: "S s_full seen", 1: "S ldB+max", 2: "S ldA+max", 3: "S rescale chk", 4: "S exps A", 5: "S stA ldB expsB", 6: "S stB waited", 7: "S arrived", 10: "M p_full seen", 11: "M PV issued+commit"}
-    for j in range(3):
-        print("  iter", 8 + j, " ".join(f"[{names[k]} {int(ev[j, k]) - t0}]" for k in (8, 9, 0, 1, 2, 3, 4, 5, 6, 7, 10, 11)))
+        print(f"  warp {2 if w == 0 else 7}: " + "  ".join(f"{n}={v:.0f}" for n, v in zip(PHASES, m.tolist())) + f"  | total/tile={m.sum():.0f} clk")
 
-#probe(0, ["wait s_full", "ld B+max", "ld A+max", "rescale", "exps A", "st A, ld B, exps B", "st B+wait", "arrive"], "s1")
+
+def trace():
+    buf = torch.zeros(8 * 16, dtype=torch.int64, device=dev)
+    ops.lib.glg_debug_attn_poly(64)
+    ops.lib.glg_debug_attn_probe(buf.data_ptr())
+    run()
+    torch.cuda.synchronize()
+    buf.zero_()
+    run()
+    torch.cuda.synchronize()
+    ops.lib.glg_debug_attn_probe(None)
+    ops.lib.glg_debug_attn_poly(0)
+    ev = buf.view(8, 16).cpu()
+    t0 = int(ev[0, 5])
+    names = ["TMA kv_empty ok->load", "MMA kv_full ok", "MMA QK issued", "MMA p_full seen", "MMA PV issued", "SM s_full seen", "SM arrived p_full"]
+    print("event trace, CTA 0; columns = key tile 8..15; clk relative to softmax s_full(8) seen")
+    for k, n in enumerate(names):
+        print(f"  {n:24s}" + " ".join(f"{int(ev[j, k]) - t0:7d}" for j in range(8)))
+
+
+phases(0, "all on")
+phases(1, "no MUFU")
+trace()
+ops.lib.glg_debug_attn_tc_variant(0)

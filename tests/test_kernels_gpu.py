@@ -247,11 +247,11 @@ ATTN_CASES = [
 @pytest.mark.parametrize("path", ["auto", "mma_sync", "tcgen05"])
 def test_attention(ops, ref, B, heads, d, Lq, Lk, mode, path):
     """path=auto: tcgen05/TMEM kernel for d_head <= 128 and > 128 keys, the K/V-resident mma.sync kernel for short key
-    sets (text context), the streaming mma.sync kernel for d_head > 128 (auto picks the one-thread-per-row tcgen05
-    kernel for d_head <= 64 and the row-pair one above); the other two values force mma.sync / the row-pair kernel."""
+    sets (text context), the streaming mma.sync kernel for d_head > 128; the other values force mma.sync and the
+    tcgen05 kernel with softmax-side row sums (no ones column)."""
     if path != "auto" and d > 128:
         pytest.skip("same kernel as auto")
-    if path == "tcgen05" and Lk > 128 and d > 64:
+    if path == "tcgen05" and Lk > 128 and d % 16 == 0:
         pytest.skip("same kernel as auto")
     C = heads * d
     if mode == "qkv":
@@ -269,7 +269,8 @@ def test_attention(ops, ref, B, heads, d, Lq, Lk, mode, path):
     out = torch.zeros(B, Lq, C, device="cuda:0", dtype=torch.bfloat16)
     out_r = torch.zeros_like(out)
     ops.lib.glg_debug_attn_mode({"auto": 0, "mma_sync": 1, "tcgen05": 2}[path])
-    ops.lib.glg_debug_attn_tc_variant(1 if path == "tcgen05" else 0)     # 1: the row-pair kernel also for d_head <= 64
+    # 3: tcgen05 kernel with the softmax-side row sum (auto uses the ones-column row sum when d_head % 16 != 0)
+    ops.lib.glg_debug_attn_tc_variant(3 if path == "tcgen05" else 0)
     try:
         ops.attention(q, k, v, out, heads, d)
         torch.cuda.synchronize()
