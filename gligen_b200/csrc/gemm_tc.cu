@@ -610,7 +610,7 @@ static void pick_tile(int M, int N, int num_kb, bool geglu, bool conv, int max_s
   for (int pair = 0; pair < 2; ++pair) {
     if (pair && (g_cta2_mode == 1 || M <= 128)) continue;
     // measured on B200 (profiles/): pairing pays only for large, long-K, N % 256 == 0 problems; the 3x3 convs tie
-    if (pair && g_cta2_mode == 0 && (conv || N % 256 || num_kb < 16 || M < 2048)) continue;
+    if (pair && g_cta2_mode == 0 && (conv || N % 256 || num_kb < 16 || M < 4096)) continue;      // (sweep_bn: M = 2048 pairs lose 20 %)
     if (!pair && g_cta2_mode == 2 && M > 128) {
       bool any = false;
       for (int i = 0; i < 3; ++i) any |= (N % cands[i] == 0) && (!geglu || cands[i] == 256);
@@ -636,7 +636,7 @@ static void pick_tile(int M, int N, int num_kb, bool geglu, bool conv, int max_s
         const int waves = (tiles * sp + units - 1) / units;
         const int kb_cta = (num_kb + sp - 1) / sp;
         float t = (float)waves * (per_kb * kb_cta + 3000.0f);
-        if (sp > 1) t += 5000.0f + (float)sp * M * N * 4.0f / (sms * 40.0f);
+        if (sp > 1) t += 12000.0f + (float)sp * M * N * 4.0f / (sms * 40.0f);     // slab round trip + reduce launch (sweep_bn)
         const int ctas = (pair ? 2 : 1) * (tiles * sp < units ? tiles * sp : units);
         t *= 1.0f + 0.10f * (1.0f - (float)ctas / (float)sms);     // idle SMs: prefer the finer decomposition
         if (t < best) { best = t; best_bn = bn; best_pair = pair; best_s = sp; }

@@ -17,7 +17,7 @@ if [ "$2" == "--profile" ]; then
       python bench.py --steps 1 --warmup 1 --plms-steps 1 --no-cpu-baseline --no-kernel-pass > gpurun_out/ncu_gemm_$TAG.log 2>&1
   tail -n 2 gpurun_out/ncu_gemm_$TAG.log
   echo "== ncu full: attention"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_fwd -s 100 -c 2 -o gpurun_out/prof_attn_$TAG -f \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_tc_kernel -s 10 -c 2 -o gpurun_out/prof_attn_$TAG -f \
       python bench.py --steps 1 --warmup 1 --plms-steps 1 --no-cpu-baseline --no-kernel-pass > gpurun_out/ncu_attn_$TAG.log 2>&1
   tail -n 2 gpurun_out/ncu_attn_$TAG.log
 fi
