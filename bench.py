@@ -360,7 +360,7 @@ def main():
         roof["whole_step_achieved"] = f_img * value / world / 1e12
         roof["whole_step_frac"] = roof["whole_step_achieved"] / peak_tf
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:          # reported at N = 1 only (rank 0's host cores)
             if sd is None:
                 sd = synthetic_state_dict(cfg, seed=0)
             t_fw, cores = cpu_forward_seconds(cfg, sd, args.max_objs, args.cpu_forwards)
