@@ -363,309 +363,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 }
 
 
-// ---------------------------------------------------------------------------------------------------------------
-// Head dims <= 64, long key sets (the 64x64-latent self attention: 80 % of all attention time): two query tiles per CTA.
-//
-// profiles/r1_attention_pipeline.md: the row-pair kernel above is paced by its softmax warps, and what they spend is
-// not exp2 throughput but the fixed cost of every hand-off (mbarrier wait, tcgen05.ld/st issue, smem exchange, vote:
-// ~550 clk) once per 32 scores per thread.  This layout pays the hand-offs once per 128 scores per thread:
-//   * key tiles of 128, one thread per query row (no max exchange), scores read twice from TMEM (max pass, exp pass)
-//     in 32-column chunks, so registers stay modest;
-//   * two 128-query tiles A, B per CTA with their own S (128 fp32 columns, P aliases its first half) and O (<= 64):
-//     384 of the 512 TMEM columns, one CTA per SM.  The MMA warp alternates A and B (QK^T_A, QK^T_B, then per key tile
-//     P.V_A, QK^T_A(next), P.V_B, QK^T_B(next)), so while one warpgroup runs its exp2 pass the tensor pipe turns the
-//     other one's tile around: the two warps that share a sub-partition's MUFU take turns instead of colliding;
-//   * S_X(j+1) is committed behind P.V_X(j) on the in-order tensor pipe, so "S ready" also means "O stable": the lazy
-//     O rescale needs no extra barrier.
-namespace atc2 {
-constexpr int BM = 128, BN = 128, STAGES = 3;
-constexpr int Q_BYTES = BM * 64 * 2;        // one query tile (16 KB)
-constexpr int KV_BYTES = BN * 64 * 2;       // K (or V) of one stage (16 KB)
-constexpr int TMEM_COLS = 512;
-constexpr int S_COL = 0, O_COL = 256;       // S_A 0..127 | S_B 128..255 | O_A 256..319 | O_B 320..383
-constexpr int SMEM_BYTES = 2 * Q_BYTES + STAGES * 2 * KV_BYTES + 1024 + 256;
-}  // namespace atc2
-
-template <int DPAD, bool ONES>   // DPAD in {16, 32, 48, 64}
-__global__ void __launch_bounds__(320, 1)
-attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
-  using namespace atc2;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = base;                                   // tile A | tile B
-  const uint32_t sKV = base + 2 * Q_BYTES;                    // per stage: K | V
-  const uint32_t bar_base = sKV + STAGES * 2 * KV_BYTES;
-  const uint32_t q_full = bar_base;
-  auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
-  auto kv_empty = [&](int s) { return bar_base + 8u * (1 + STAGES + s); };
-  auto s_full = [&](int x) { return bar_base + 8u * (1 + 2 * STAGES + x); };
-  auto p_full = [&](int x) { return bar_base + 8u * (3 + 2 * STAGES + x); };
-  const uint32_t o_full = bar_base + 8u * (5 + 2 * STAGES);
-  const uint32_t tmem_slot = bar_base + 8u * (6 + 2 * STAGES);
-
-  pdl_trigger();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 2 * BM;
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int nkt = (p.Lk + BN - 1) / BN;
-
-  if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-    for (int x = 0; x < 2; ++x) { mbar_init(s_full(x), 1); mbar_init(p_full(x), 4); }
-    mbar_init(o_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) {
-    if (lane == 0) { tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); }
-    __syncwarp();
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  pdl_wait();
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    const bool leader = elect_one();
-    if (leader) {
-      mbar_arrive_expect_tx(q_full, 2 * Q_BYTES);
-      tma_load_4d(sQ, &tmQ, q_full, 0, h, q0, b);
-      tma_load_4d(sQ + Q_BYTES, &tmQ, q_full, 0, h, q0 + BM, b);
-    }
-    int stage = 0; uint32_t phase = 0;
-    for (int j = 0; j < nkt; ++j) {
-      mbar_wait(kv_empty(stage), phase ^ 1u);
-      if (leader) {
-        mbar_arrive_expect_tx(kv_full(stage), 2 * KV_BYTES);
-        const uint32_t sk = sKV + stage * 2 * KV_BYTES;
-        tma_load_4d(sk, &tmK, kv_full(stage), 0, h, j * BN, b);
-        tma_load_4d(sk + KV_BYTES, &tmV, kv_full(stage), 0, h, j * BN, b);
-      }
-      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc_s = umma_idesc_bf16(128, BN);
-    constexpr uint32_t idesc_o = umma_idesc_bf16(128, DPAD, true);
-    const bool leader = elect_one();
-    mbar_wait(q_full, 0);
-    tc_fence_after();
-    // K_j / V_j have landed: (ONES) write 1.0 into column d_head of V_j, then the tile may be used
-    auto kv_ready = [&](int j) {
-      const int stage = j % STAGES;
-      mbar_wait(kv_full(stage), (uint32_t)((j / STAGES) & 1));
-      tc_fence_after();
-      if constexpr (ONES) {
-        const uint32_t svt = sKV + stage * 2 * KV_BYTES + KV_BYTES;
-#pragma unroll
-        for (int r = lane; r < BN; r += 32) {
-          const uint32_t a = svt + (uint32_t)r * 128u + ((((uint32_t)p.d >> 3) ^ ((uint32_t)r & 7u)) << 4);
-          asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)0x3F80) : "memory");
-        }
-        fence_proxy_async();
-        __syncwarp();
-      }
-    };
-    auto issue_qk = [&](int x, int j) {        // S_x = Q_x K_j^T
-      const uint32_t sk = sKV + (j % STAGES) * 2 * KV_BYTES;
-      if (leader) {
-#pragma unroll
-        for (int kk = 0; kk < DPAD / 16; ++kk)
-          umma_bf16(tmem_base + S_COL + x * BN, umma_desc_kmajor_sw128(sQ + x * Q_BYTES) + 2 * kk,
-                    umma_desc_kmajor_sw128(sk) + 2 * kk, idesc_s, kk != 0 ? 1u : 0u);
-        umma_commit(s_full(x));                 // behind P.V_x(j-1): also tells the softmax warps that O_x is stable
-      }
-    };
-    auto issue_pv = [&](int x, int j) {         // O_x += P_x V_j
-      mbar_wait(p_full(x), (uint32_t)(j & 1));
-      tc_fence_after();
-      const uint64_t vdesc = umma_desc_mnmajor_sw128(sKV + (j % STAGES) * 2 * KV_BYTES + KV_BYTES, KV_BYTES);
-      if (leader) {
-#pragma unroll
-        for (int k = 0; k < BN / 16; ++k)       // 16 keys per step: +8 TMEM columns of P, +16 rows (2048 B) of V
-          umma_bf16_ts(tmem_base + O_COL + x * 64, tmem_base + S_COL + x * BN + 8 * k, vdesc + 128 * k, idesc_o,
-                       (j | k) != 0 ? 1u : 0u);
-      }
-    };
-    kv_ready(0);
-    issue_qk(0, 0);
-    issue_qk(1, 0);
-    for (int j = 0; j < nkt; ++j) {
-      issue_pv(0, j);
-      if (j + 1 < nkt) { kv_ready(j + 1); issue_qk(0, j + 1); }
-      issue_pv(1, j);
-      if (leader) umma_commit(kv_empty(j % STAGES));          // K_j, V_j fully consumed
-      if (j + 1 < nkt) issue_qk(1, j + 1);
-    }
-    if (leader) umma_commit(o_full);
-  } else {
-    // ===================== softmax / correction / output: warps 2-5 own tile A, 6-9 tile B; thread == query row ======
-    const int x = (warp - 2) >> 2;               // query tile
-    const int q = warp & 3;                      // TMEM lane quarter
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t s_col = lane_base + S_COL + x * BN;
-    const uint32_t o_col = lane_base + O_COL + x * 64;
-    const int row = q0 + x * BM + q * 32 + lane;
-    const float sl2 = p.scale_log2;
-    const bool ragged = (p.Lk & (BN - 1)) != 0;
-    float m_ref = -INFINITY, l = 0.f;
-    // MUFU turn-taking (named barriers 2 + x, 256 = both warpgroups): a warpgroup runs its exp2 pass only while it holds
-    // the turn and hands it over afterwards, so the two warps that share a sub-partition's MUFU alternate - one does
-    // exp2 at full rate while the other waits for its MMAs, reads its next scores and finds its row maxima.
-    auto turn_wait = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(2 + x) : "memory"); };
-    auto turn_pass = [&]() { asm volatile("bar.arrive %0, 256;" ::"r"(2 + (x ^ 1)) : "memory"); };
-    if (x == 1) turn_pass();                     // tile A goes first
-    for (int j = 0; j < nkt; ++j) {
-      mbar_wait(s_full(x), (uint32_t)(j & 1));
-      tc_fence_after();
-      const bool mask = ragged && j == nkt - 1;
-      const int valid = p.Lk - j * BN;           // keys [valid, 128) of this tile are padding (only if mask)
-      // ---- pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 4; c += 2) {
-        uint32_t s0[32], s1[32];
-        tmem_ld32(s_col + c * 32, s0);
-        tmem_ld32(s_col + c * 32 + 32, s1);
-        tmem_ld_wait();
-        if (mask) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (c * 32 + i >= valid) s0[i] = 0xff800000u;
-            if (c * 32 + 32 + i >= valid) s1[i] = 0xff800000u;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
-      }
-      const float m_new = fmaxf(m_ref, mx);
-      if (j == 0) {
-        m_ref = m_new;
-      } else {
-        const bool need = (m_new - m_ref) * sl2 > atc::RESCALE_THRESHOLD;
-        if (__any_sync(0xffffffffu, need)) {     // tcgen05.ld/st are warp-collective: the whole warp rescales
-          const float f = need ? ex2_approx((m_ref - m_new) * sl2) : 1.0f;
-          if (need) { m_ref = m_new; if constexpr (!ONES) l *= f; }
-#pragma unroll
-          for (int c = 0; c < DPAD / 16; ++c) {
-            uint32_t o[16];
-            tmem_ld16(o_col + c * 16, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-            tmem_st16(o_col + c * 16, o);
-          }
-        }
-      }
-      // ---- pass 2: P = exp2(s * scale - m) as bf16 into the first 64 columns of S (chunk c -> columns 16c..16c+15:
-      //      always columns whose scores this thread has already consumed)
-      const float ms = m_ref * sl2;
-      float sum = 0.f;
-      uint32_t sv[32];
-      tmem_ld32(s_col, sv);
-      tmem_ld_wait();
-      turn_wait();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t nx[32];
-        if (c < 3) tmem_ld32(s_col + (c + 1) * 32, nx);       // next chunk in flight during this chunk's exp2
-        if (mask) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) if (c * 32 + i >= valid) sv[i] = 0xff800000u;
-        }
-        // three separate sweeps (arguments, exp2, pack): 32 independent MUFUs back to back keep the XU pipe full from a
-        // single warp; interleaved per element the FFMA -> MUFU -> F2FP dependencies leave it idle a third of the time
-        float e[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) e[i] = fmaf(__uint_as_float(sv[i]), sl2, -ms);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) e[i] = ex2_approx(e[i]);
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if constexpr (!ONES) sum += e[2 * i] + e[2 * i + 1];
-          pk[i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
-        }
-        if (c < 3) {
-          tmem_ld_wait();                                     // chunk c+1 (columns >= 32(c+1)) is in registers ...
-#pragma unroll
-          for (int i = 0; i < 32; ++i) sv[i] = nx[i];
-        }
-        tmem_st16(s_col + c * 16, pk);                        // ... before P_c lands on columns < 16(c+1)
-      }
-      turn_pass();
-      if constexpr (!ONES) l += sum;
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full(x));
-    }
-    // ---- epilogue: O / l -> bf16
-    mbar_wait(o_full, 0);
-    tc_fence_after();
-    float inv;
-    if constexpr (ONES) {
-      const uint32_t lsum = tmem_ld1(o_col + p.d);            // column d_head of O = sum_j P_j . 1
-      tmem_ld_wait();
-      inv = 1.0f / __uint_as_float(lsum);
-    } else {
-      inv = 1.0f / l;
-    }
-    bf16* orow = p.o + (long long)b * p.o_batch + (long long)row * p.o_row + (long long)h * p.d;
-#pragma unroll
-    for (int c = 0; c < DPAD / 16; ++c) {
-      uint32_t o[16];
-      tmem_ld16(o_col + c * 16, o);
-      tmem_ld_wait();
-      if (row < p.Lq) {
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int col = c * 16 + g * 8;
-          if (col < p.d) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
-            u.y = pack_bf16x2(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
-            u.z = pack_bf16x2(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
-            u.w = pack_bf16x2(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
-            *reinterpret_cast<uint4*>(orow + col) = u;
-          }
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    __syncwarp();
-    tc_fence_after();
-    tmem_dealloc(tmem_base, atc2::TMEM_COLS);
-  }
-}
-
-template <int DPAD, bool ONES>
-static int launch_attn_tc2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p, int B, cudaStream_t st) {
-  static bool attr_set = false;
-  auto kern = attn_tc2_kernel<DPAD, ONES>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, atc2::SMEM_BYTES);
-    if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(attn_tc2): ") + cudaGetErrorString(e));
-    attr_set = true;
-  }
-  dim3 grid((p.Lq + 2 * atc2::BM - 1) / (2 * atc2::BM), p.heads, B);
-  launch_k(kern, grid, dim3(320), atc2::SMEM_BYTES, st, 1, tq, tk, tv, p);
-  count_launch();
-  return check_launch("attention_tc2 launch");
-}
-
-int g_attn_tc_variant = 0;     // test hook: 0 = auto, 1 = row-pair kernel (PROBE build where asked, scripts/micro), 3 = row-pair kernel without
-                               // the ones-column row sum, 4 = two-query-tile kernel without the ones column
+int g_attn_tc_variant = 0;     // test hook: 0 = auto, 1 = PROBE build where asked (scripts/micro), 3 = no ones-column row sum
 int g_attn_dbg = 0;            // PROBE build only: knock-out flags (1 MUFU, 2 QK^T MMAs, 4 P.V MMAs, 16 K/V TMA), 64 = event trace
 
 long long* g_attn_probe = nullptr;
@@ -714,23 +412,6 @@ int attention_tc(const GlgAttnArgs* a, cudaStream_t st) {
   p.dbg = g_attn_dbg;
   const int dpad = (a->d_head + 15) / 16 * 16;
   const bool ones = a->d_head < dpad && g_attn_tc_variant != 3;      // a spare V column carries the row sum
-  if (dpad <= 64 && a->Lk > 2 * atc2::BN && (g_attn_tc_variant == 0 || g_attn_tc_variant == 4)) {
-    // two-query-tile kernel: K/V tiles of 128 keys need their own tensor maps
-    CUtensorMap tk2, tv2;
-    const uint64_t dims[4] = {d, hd, (uint64_t)a->Lk, (uint64_t)a->B};
-    const uint64_t strk[3] = {d * 2, (uint64_t)a->k_row * 2, (uint64_t)a->k_batch * 2};
-    const uint64_t strv[3] = {d * 2, (uint64_t)a->v_row * 2, (uint64_t)a->v_batch * 2};
-    const uint32_t box[4] = {64, 1, (uint32_t)atc2::BN, 1};
-    if (get_tmap_bf16(&tk2, a->k, 4, dims, strk, box)) return -1;
-    if (get_tmap_bf16(&tv2, a->v, 4, dims, strv, box)) return -1;
-    const bool ones2 = ones && g_attn_tc_variant != 4;
-    switch (dpad) {
-      case 16: return ones2 ? launch_attn_tc2<16, true>(tq, tk2, tv2, p, a->B, st) : launch_attn_tc2<16, false>(tq, tk2, tv2, p, a->B, st);
-      case 32: return ones2 ? launch_attn_tc2<32, true>(tq, tk2, tv2, p, a->B, st) : launch_attn_tc2<32, false>(tq, tk2, tv2, p, a->B, st);
-      case 48: return ones2 ? launch_attn_tc2<48, true>(tq, tk2, tv2, p, a->B, st) : launch_attn_tc2<48, false>(tq, tk2, tv2, p, a->B, st);
-      case 64: return ones2 ? launch_attn_tc2<64, true>(tq, tk2, tv2, p, a->B, st) : launch_attn_tc2<64, false>(tq, tk2, tv2, p, a->B, st);
-    }
-  }
   switch (dpad) {
     case 16: return ones ? launch_attn_tc<16, false, true>(tq, tk, tv, p, a->B, st) : launch_attn_tc<16>(tq, tk, tv, p, a->B, st);
     case 32: return ones ? launch_attn_tc<32, false, true>(tq, tk, tv, p, a->B, st) : launch_attn_tc<32>(tq, tk, tv, p, a->B, st);

@@ -240,27 +240,24 @@ ATTN_CASES = [
     (2, 8, 40, 1000, 128, "kv"),          # short-key kernel: ragged last query tile of a 4-tile CTA, two full K tiles
     (2, 8, 80, 257, 1, "kv"),
     (1, 8, 160, 320, 65, "kv"),
-    (2, 8, 40, 300, 257, "plain"),         # two-query-tile kernel: ragged second query tile, 3 key tiles (last: 1 key)
+    (2, 8, 40, 300, 257, "plain"),         # ragged query tile, 5 key tiles (last: 1 key)
     (1, 8, 24, 512, 1000, "plain"),
     (1, 4, 64, 257, 384, "plain"),
 ]
 
 
 @pytest.mark.parametrize("B,heads,d,Lq,Lk,mode", ATTN_CASES)
-@pytest.mark.parametrize("path", ["auto", "mma_sync", "tc_pair", "tc_pair_sum", "tc2_sum"])
+@pytest.mark.parametrize("path", ["auto", "mma_sync", "tcgen05", "tcgen05_sum"])
 def test_attention(ops, ref, B, heads, d, Lq, Lk, mode, path):
-    """auto: two-query-tile tcgen05 kernel (d_head <= 64, > 256 keys), row-pair tcgen05 kernel (other d_head <= 128,
-    > 128 keys), K/V-resident mma.sync kernel (<= 128 keys: text context), streaming mma.sync kernel (d_head > 128).
-    Row sums come from a ones column of V when d_head % 16 != 0.  The other paths force one kernel / the softmax-side sum."""
-    two_tile = d <= 64 and Lk > 256
-    if path == "mma_sync" and d > 128:
+    """auto: tcgen05 kernel (d_head <= 128, > 128 keys), K/V-resident mma.sync kernel (<= 128 keys: text context),
+    streaming mma.sync kernel (d_head > 128).  Row sums come from a ones column of V when d_head % 16 != 0.
+    The other paths force mma.sync / tcgen05 (also for short key sets) / tcgen05 with the softmax-side row sum."""
+    if path != "auto" and d > 128:
         pytest.skip("same kernel as auto")
-    if path.startswith("tc_pair") and (d > 128 or (path == "tc_pair" and Lk > 128 and not two_tile) or (path == "tc_pair_sum" and d % 16 == 0 and Lk > 128 and not two_tile)):
-        pytest.skip("not applicable / same kernel as auto")
-    if path == "tc_pair_sum" and d % 16 == 0 and two_tile:
-        pytest.skip("same kernel as tc_pair")
-    if path == "tc2_sum" and not (two_tile and d % 16 != 0):
+    if path == "tcgen05" and Lk > 128:
         pytest.skip("same kernel as auto")
+    if path == "tcgen05_sum" and d % 16 == 0:
+        pytest.skip("same kernel as tcgen05 / auto")
     C = heads * d
     if mode == "qkv":
         qkv = rnd(B, Lk, 3 * C)
@@ -276,8 +273,8 @@ def test_attention(ops, ref, B, heads, d, Lq, Lk, mode, path):
         q, k, v = rnd(B, Lq, C), rnd(B, Lk, C, seed=1), rnd(B, Lk, C, seed=2)
     out = torch.zeros(B, Lq, C, device="cuda:0", dtype=torch.bfloat16)
     out_r = torch.zeros_like(out)
-    ops.lib.glg_debug_attn_mode({"auto": 0, "mma_sync": 1, "tc_pair": 2, "tc_pair_sum": 2, "tc2_sum": 0}[path])
-    ops.lib.glg_debug_attn_tc_variant({"auto": 0, "mma_sync": 0, "tc_pair": 1, "tc_pair_sum": 3, "tc2_sum": 4}[path])
+    ops.lib.glg_debug_attn_mode({"auto": 0, "mma_sync": 1, "tcgen05": 2, "tcgen05_sum": 2}[path])
+    ops.lib.glg_debug_attn_tc_variant(3 if path == "tcgen05_sum" else 0)
     try:
         ops.attention(q, k, v, out, heads, d)
         torch.cuda.synchronize()
