@@ -18,6 +18,75 @@ static inline unsigned blocks_for(long long n, int threads) {
 }
 
 // ---- first conv: NCHW fp32 (x | extra) -> NHWC bf16.  w packed [9][Cin][Cout] fp32. -----------------
+// Wide-latent variant (W % 4 == 0, weights fit shared memory): persistent blocks stage the whole [9][Cin][Cout] fp32
+// weight once; a thread owns 4 consecutive pixels x 8 output channels, so every weight vector read from smem feeds 32
+// FMAs and every input row segment (6 values) feeds three taps.
+__global__ void __launch_bounds__(256) conv_in_px4_kernel(const float* __restrict__ x, int C0, const float* __restrict__ extra, int C1,
+                                   const float* __restrict__ w, const float* __restrict__ bias, bf16* __restrict__ out,
+                                   long long ldo, int B, int H, int W, int Cout) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float cin_sw[];      // [9 * Cin][Cout]
+  const int Cin = C0 + C1;
+  const int nw4 = 9 * Cin * Cout / 4;
+  for (int i = threadIdx.x; i < nw4; i += blockDim.x)
+    reinterpret_cast<float4*>(cin_sw)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
+  __syncthreads();
+  const int cov = Cout >> 3, Wq = W >> 2;
+  const long long total = (long long)B * H * Wq * cov;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cov);
+    const long long g = i / cov;
+    const int x0 = (int)(g % Wq) * 4;
+    const int yh = (int)((g / Wq) % H);
+    const int b = (int)(g / ((long long)Wq * H));
+    float acc[4][8];
+    {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8 + 4));
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        acc[px][0] = b0.x; acc[px][1] = b0.y; acc[px][2] = b0.z; acc[px][3] = b0.w;
+        acc[px][4] = b1.x; acc[px][5] = b1.y; acc[px][6] = b1.z; acc[px][7] = b1.w;
+      }
+    }
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = yh + dy - 1;
+      if (yy < 0 || yy >= H) continue;
+      for (int ci = 0; ci < Cin; ++ci) {
+        const float* row = ci < C0 ? x + (((long long)b * C0 + ci) * H + yy) * W : extra + (((long long)b * C1 + (ci - C0)) * H + yy) * W;
+        float r[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const int xx = x0 + k - 1;
+          r[k] = (xx >= 0 && xx < W) ? __ldg(row + xx) : 0.f;
+        }
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float* wp = cin_sw + ((dy * 3 + dx) * Cin + ci) * Cout + c8 * 8;
+          const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
+#pragma unroll
+          for (int px = 0; px < 4; ++px) {
+            const float v = r[px + dx];
+            acc[px][0] = fmaf(v, w0.x, acc[px][0]); acc[px][1] = fmaf(v, w0.y, acc[px][1]);
+            acc[px][2] = fmaf(v, w0.z, acc[px][2]); acc[px][3] = fmaf(v, w0.w, acc[px][3]);
+            acc[px][4] = fmaf(v, w1.x, acc[px][4]); acc[px][5] = fmaf(v, w1.y, acc[px][5]);
+            acc[px][6] = fmaf(v, w1.z, acc[px][6]); acc[px][7] = fmaf(v, w1.w, acc[px][7]);
+          }
+        }
+      }
+    }
+    const long long pix0 = ((long long)b * H + yh) * W + x0;
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      uint4 u;
+      u.x = pack_bf16x2(acc[px][0], acc[px][1]); u.y = pack_bf16x2(acc[px][2], acc[px][3]);
+      u.z = pack_bf16x2(acc[px][4], acc[px][5]); u.w = pack_bf16x2(acc[px][6], acc[px][7]);
+      *reinterpret_cast<uint4*>(out + (pix0 + px) * ldo + c8 * 8) = u;
+    }
+  }
+}
+
 __global__ void conv_in_kernel(const float* __restrict__ x, int C0, const float* __restrict__ extra, int C1,
                                const float* __restrict__ w, const float* __restrict__ bias, bf16* __restrict__ out,
                                long long ldo, int B, int H, int W, int Cout) {
@@ -55,6 +124,65 @@ __global__ void conv_in_kernel(const float* __restrict__ x, int C0, const float*
 }
 
 // ---- last conv: NHWC bf16 -> NCHW fp32, Cout <= 8.  w packed [9][Cout][Cin] fp32.  One warp per pixel.
+// Wide-latent variant (W % 8 == 0): one warp owns 8 consecutive pixels, so each weight vector it loads is used for
+// 8 pixels (the per-pixel kernel below re-reads all 9 x COUT x Cin weights for every pixel).
+template <int COUT>
+__global__ void __launch_bounds__(256) conv_out_px8_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ w,
+                                    const float* __restrict__ bias, float* __restrict__ out, int B, int H, int W, int Cin) {
+  pdl_trigger();
+  pdl_wait();
+  const int Wo = W >> 3;
+  const long long grp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (grp >= (long long)B * H * Wo) return;
+  const int lane = threadIdx.x & 31;
+  const int x0 = (int)(grp % Wo) * 8;
+  const int yh = (int)((grp / Wo) % H);
+  const int b = (int)(grp / ((long long)Wo * H));
+  float acc[8][COUT];
+#pragma unroll
+  for (int px = 0; px < 8; ++px)
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) acc[px][j] = 0.f;
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = yh + tap / 3 - 1, dx = tap % 3 - 1;
+    if (yy < 0 || yy >= H) continue;
+    const bf16* xrow = x + (((long long)b * H + yy) * W) * ldx;
+    for (int c = lane * 8; c < Cin; c += 256) {
+      float wv[COUT][8];
+#pragma unroll
+      for (int co = 0; co < COUT; ++co) {
+        const float* wp = w + ((long long)tap * COUT + co) * Cin + c;
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp)), w1 = __ldg(reinterpret_cast<const float4*>(wp + 4));
+        wv[co][0] = w0.x; wv[co][1] = w0.y; wv[co][2] = w0.z; wv[co][3] = w0.w;
+        wv[co][4] = w1.x; wv[co][5] = w1.y; wv[co][6] = w1.z; wv[co][7] = w1.w;
+      }
+#pragma unroll
+      for (int px = 0; px < 8; ++px) {
+        const int xx = x0 + px + dx;
+        if (xx < 0 || xx >= W) continue;
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(xrow + (long long)xx * ldx + c));
+        float v[8];
+        float2 f;
+        f = unpack_bf16x2(u.x); v[0] = f.x; v[1] = f.y;
+        f = unpack_bf16x2(u.y); v[2] = f.x; v[3] = f.y;
+        f = unpack_bf16x2(u.z); v[4] = f.x; v[5] = f.y;
+        f = unpack_bf16x2(u.w); v[6] = f.x; v[7] = f.y;
+#pragma unroll
+        for (int co = 0; co < COUT; ++co)
+          acc[px][co] += v[0] * wv[co][0] + v[1] * wv[co][1] + v[2] * wv[co][2] + v[3] * wv[co][3] + v[4] * wv[co][4] +
+                         v[5] * wv[co][5] + v[6] * wv[co][6] + v[7] * wv[co][7];
+      }
+    }
+  }
+#pragma unroll
+  for (int px = 0; px < 8; ++px)
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+      const float sum = warp_sum(acc[px][co]);
+      if (lane == ((px * COUT + co) & 31)) out[(((long long)b * COUT + co) * H + yh) * W + x0 + px] = sum + bias[co];
+    }
+}
+
 template <int COUT>
 __global__ void conv_out_kernel(const bf16* __restrict__ x, long long ldx, const float* __restrict__ w,
                                 const float* __restrict__ bias, float* __restrict__ out, int B, int H, int W, int Cin) {
@@ -227,7 +355,21 @@ extern "C" int glg_conv_in(const float* x, int32_t C0, const float* extra, int32
   if (Cout % 8 || ldo % 8) return set_error("glg_conv_in: Cout and ldo must be multiples of 8");
   if (C1 > 0 && !extra) return set_error("glg_conv_in: extra channels requested but pointer is null");
   const long long total = (long long)B * H * Wd * (Cout / 8);
-  launch_k(conv_in_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, ST, 1, x, C0, extra, C1, w, bias, (bf16*)out, ldo, B, H, Wd, Cout);
+  const size_t wbytes = (size_t)9 * (C0 + C1) * Cout * sizeof(float);
+  if (Wd % 4 == 0 && wbytes <= 110 * 1024 && total >= 4 * 256 * 64) {
+    static size_t attr_bytes = 0;
+    if (wbytes > attr_bytes) {
+      cudaError_t e = cudaFuncSetAttribute(conv_in_px4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes);
+      if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(conv_in): ") + cudaGetErrorString(e));
+      attr_bytes = wbytes;
+    }
+    unsigned grid = blocks_for(total / 4, 256);
+    const unsigned cap = 2u * (unsigned)num_sms();
+    if (grid > cap) grid = cap;
+    launch_k(conv_in_px4_kernel, dim3(grid), dim3(256), wbytes, ST, 1, x, C0, extra, C1, w, bias, (bf16*)out, ldo, B, H, Wd, Cout);
+  } else {
+    launch_k(conv_in_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, ST, 1, x, C0, extra, C1, w, bias, (bf16*)out, ldo, B, H, Wd, Cout);
+  }
   count_launch();
   return check_launch("conv_in launch");
 }
@@ -236,6 +378,11 @@ extern "C" int glg_conv_out(const void* x, int64_t ldx, const float* w, const fl
                             int32_t B, int32_t H, int32_t Wd, int32_t Cin, int32_t Cout, void* stream) {
   if (Cin % 8 || ldx % 8) return set_error("glg_conv_out: Cin and ldx must be multiples of 8");
   const long long pix = (long long)B * H * Wd;
+  if (Wd % 8 == 0 && Cout == 4) {
+    launch_k(conv_out_px8_kernel<4>, dim3(blocks_for(pix / 8, 8)), dim3(256), 0, ST, 1, (const bf16*)x, ldx, w, bias, out, B, H, Wd, Cin);
+    count_launch();
+    return check_launch("conv_out launch");
+  }
   const unsigned grid = blocks_for(pix, 8);
   if (Cout == 4) launch_k(conv_out_kernel<4>, dim3(grid), dim3(256), 0, ST, 1, (const bf16*)x, ldx, w, bias, out, B, H, Wd, Cin);
   else if (Cout == 8) launch_k(conv_out_kernel<8>, dim3(grid), dim3(256), 0, ST, 1, (const bf16*)x, ldx, w, bias, out, B, H, Wd, Cin);

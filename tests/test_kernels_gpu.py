@@ -340,6 +340,21 @@ def test_small_ops(ops, ref):
     ops.conv_out(x, w, b, out, 64, 64)
     ref.conv_out(x, w, b, out_r, 64, 64)
     assert_close(out, out_r, rel=2e-3, max_rel=5e-3, what="conv_out")   # torch reference conv runs in TF32
+    # odd widths take the per-pixel kernels (the wide-latent variants need W % 4 / W % 8 == 0)
+    x = rnd(2, 4, 10, 10, dtype=torch.float32)
+    w = rnd(9, 4, 64, scale=0.2, seed=2, dtype=torch.float32)
+    b = rnd(64, seed=3, dtype=torch.float32)
+    o, o_r = torch.zeros(2, 100, 64, device=dev, dtype=torch.bfloat16), torch.zeros(2, 100, 64, device=dev, dtype=torch.bfloat16)
+    ops.conv_in(x, None, w, b, o)
+    ref.conv_in(x, None, w, b, o_r)
+    assert_close(o, o_r, what="conv_in 10x10")
+    x = rnd(2, 100, 64)
+    w = rnd(9, 4, 64, scale=0.05, seed=1, dtype=torch.float32)
+    b = rnd(4, seed=2, dtype=torch.float32)
+    out, out_r = torch.zeros(2, 4, 10, 10, device=dev), torch.zeros(2, 4, 10, 10, device=dev)
+    ops.conv_out(x, w, b, out, 10, 10)
+    ref.conv_out(x, w, b, out_r, 10, 10)
+    assert_close(out, out_r, rel=2e-3, max_rel=5e-3, what="conv_out 10x10")
     # upsample / im2col
     x = rnd(2, 256, 640)
     y, y_r = torch.zeros(2, 1024, 640, device=dev, dtype=torch.bfloat16), torch.zeros(2, 1024, 640, device=dev, dtype=torch.bfloat16)
