@@ -180,7 +180,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"SD-1.4 GLIGEN box+text, 64x64 latent, PLMS {args.plms_steps} + CFG, G={args.max_objs}, alpha_type={atype}", "sample": sample},
+            "config": {"workload": f"SD-1.4 GLIGEN box+text, 64x64 latent, PLMS {args.plms_steps} + CFG {args.guidance}, batch {args.batch}/GPU, G={cfg.tokens_per_sample(args.max_objs)}, alpha_type={atype}",
+                       "forwards_per_image": n_fw, "sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
