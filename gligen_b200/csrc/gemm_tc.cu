@@ -651,6 +651,10 @@ static void pick_tile(int M, int N, int num_kb, bool geglu, bool conv, int max_s
 using namespace glg;
 
 extern "C" void glg_debug_force_bn(int bn) { glg::g_force_bn = bn; }
+// test hook (host only, no CUDA work): what the tile picker chooses for a problem; out[3] = {BN, paired CTAs, K splits}
+extern "C" void glg_debug_pick_tile(int M, int N, int K, int geglu, int conv, int can_split, long long ws_bytes, int* out) {
+  glg::pick_tile(M, N, (conv ? 9 : 1) * (K / 64), geglu != 0, conv != 0, can_split ? 8 : 1, ws_bytes, &out[0], &out[1], &out[2]);
+}
 extern "C" void glg_debug_gemm_cta2(int mode) { glg::g_cta2_mode = mode; }
 extern "C" void glg_debug_splitk(int mode) { glg::g_splitk_mode = mode; }
 

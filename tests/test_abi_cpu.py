@@ -110,3 +110,36 @@ def test_host_schedule_and_adapters():
         null = g.get_null_input()
         assert set(null) == set(out) and all(null[k].shape == out[k].shape and null[k].abs().sum() == 0 for k in out)
         assert g.get_null_input(batch=3)[next(iter(out))].shape[0] == 3
+
+
+def test_tile_picker_choices_are_valid():
+    """Host-side tile picker (csrc/gemm_tc.cu pick_tile) over every GEMM / conv shape of the SD-1.4 forward at 2B = 8
+    and at B = 1: the tile width divides N, GEGLU keeps the 256-wide interleaved tile, K is only split when allowed and
+    when each split keeps >= 16 K blocks, CTA pairs only for large plain GEMMs with N % 256 == 0."""
+    import ctypes as C
+    from gligen_b200 import lib as L
+    lib = L.load()
+    out = (C.c_int32 * 3)()
+    ws = 80 << 20
+
+    def pick(M, N, K, geglu=0, conv=0, can_split=1):
+        lib.glg_debug_pick_tile(M, N, K, geglu, conv, can_split, ws, out)
+        return out[0], out[1], out[2]
+
+    for rows in (8, 1):
+        for (T, Cc) in ((4096, 320), (1024, 640), (256, 1280), (64, 1280)):
+            M = rows * T
+            for (N, K, geglu) in ((3 * Cc, Cc, 0), (Cc, Cc, 0), (Cc, 4 * Cc, 0), (8 * Cc, Cc, 1), (2 * Cc, 768, 0)):
+                for can_split in (0, 1):
+                    bn, pair, sp = pick(M, N, K, geglu, 0, can_split)
+                    assert bn in (64, 128, 160, 256) and N % bn == 0, (M, N, K, bn)
+                    assert not geglu or bn == 256
+                    assert sp >= 1 and (can_split or sp == 1)
+                    assert sp == 1 or (K // 64) // sp >= 16
+                    assert not pair or (M >= 4096 and N % 256 == 0 and bn == 256 and sp == 1)
+        for (H, Cin, Cout) in ((64, 320, 320), (64, 960, 320), (32, 640, 640), (32, 1920, 640), (16, 1280, 1280), (16, 2560, 1280), (8, 1280, 1280), (8, 2560, 1280)):
+            bn, pair, sp = pick(rows * H * H, Cout, Cin, 0, 1, 1)
+            assert Cout % bn == 0 and not pair and sp >= 1
+            assert sp == 1 or (9 * Cin // 64) // sp >= 16
+    # the 8x8 level at 2B = 8 (M = 512) leaves most SMs idle without a K split
+    assert pick(512, 1280, 2560, 0, 1, 1)[2] > 1
