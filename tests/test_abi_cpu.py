@@ -143,3 +143,20 @@ def test_tile_picker_choices_are_valid():
             assert sp == 1 or (9 * Cin // 64) // sp >= 16
     # the 8x8 level at 2B = 8 (M = 512) leaves most SMs idle without a K split
     assert pick(512, 1280, 2560, 0, 1, 1)[2] > 1
+
+
+def test_read_official_ckpt_splits_by_prefix(tmp_path):
+    """trainer.read_official_ckpt (reference trainer.py:64-85): the key routing a real SD checkpoint goes through."""
+    import trainer
+    sd = {"model.diffusion_model.input_blocks.0.0.weight": torch.zeros(1), "cond_stage_model.transformer.x": torch.ones(1),
+          "first_stage_model.decoder.conv_in.bias": torch.zeros(2), "model_ema.decay": torch.tensor(0.9999),
+          "model_ema.num_updates": torch.tensor(3), "betas": torch.zeros(4), "alphas_cumprod": torch.ones(4)}
+    path = tmp_path / "sd.ckpt"
+    torch.save({"state_dict": sd}, path)
+    out = trainer.read_official_ckpt(str(path))
+    assert set(out) == {"model", "text_encoder", "autoencoder", "unexpected", "diffusion"}
+    assert list(out["model"]) == ["input_blocks.0.0.weight"]
+    assert list(out["text_encoder"]) == ["transformer.x"]
+    assert list(out["autoencoder"]) == ["decoder.conv_in.bias"]
+    assert sorted(out["unexpected"]) == ["model_ema.decay", "model_ema.num_updates"]
+    assert sorted(out["diffusion"]) == ["alphas_cumprod", "betas"]

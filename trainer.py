@@ -4,18 +4,19 @@ import torch
 
 
 def read_official_ckpt(ckpt_path):
-    """Split an official SD checkpoint by key prefix into model / text_encoder / autoencoder / unexpected."""
+    """Split an official SD checkpoint by key prefix (reference trainer.py:64-85): UNet keys -> "model", CLIP ->
+    "text_encoder", VAE -> "autoencoder", the two EMA counters -> "unexpected", everything else (schedule buffers) ->
+    "diffusion"."""
     state_dict = torch.load(ckpt_path, map_location="cpu")["state_dict"]
     out = {"model": {}, "text_encoder": {}, "autoencoder": {}, "unexpected": {}, "diffusion": {}}
-    prefixes = (("model.diffusion_model.", "model"), ("cond_stage_model.", "text_encoder"), ("first_stage_model.", "autoencoder"))
+    prefixes = (("model.diffusion_model", "model"), ("cond_stage_model", "text_encoder"), ("first_stage_model", "autoencoder"))
     for k, v in state_dict.items():
         for pre, name in prefixes:
             if k.startswith(pre):
-                out[name][k[len(pre):]] = v
+                out[name][k.replace(pre + ".", "")] = v
                 break
         else:
-            out["unexpected"][k] = v
-    out["diffusion"] = None
+            out["unexpected" if k in ("model_ema.decay", "model_ema.num_updates") else "diffusion"][k] = v
     return out
 
 
