@@ -376,6 +376,13 @@ def main():
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             with open(os.path.join(ROOT, "gpurun_out", "bench_per_op.json"), "w") as f:
                 json.dump([dict(name=n, kind=k, gflop=fl / 1e9, mbytes=by / 1e6, ms=m) for n, k, fl, by, m in per_op], f)
+        tpath = os.path.join(ROOT, "profiles", "r1_gemm_dram_traffic.json")
+        if os.path.exists(tpath):                  # measured once with ncu (bench.py cannot run under a profiler itself)
+            tr = json.load(open(tpath))
+            roof["traffic"] = tr["dram_bytes_read_per_launch"] + tr["dram_bytes_write_per_launch"]
+            roof["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per gemm_tc_kernel launch, mean of "
+                                    f"{tr['launches']} launches (profiles/r1_gemm_dram_traffic.json); algorithmic minimum "
+                                    f"{tr['algorithmic_bytes_per_launch']:.3g} B/launch - L2 (126 MB) keeps producer->consumer activations off DRAM")
         roof["whole_step_achieved"] = f_img * value / world / 1e12
         roof["whole_step_frac"] = roof["whole_step_achieved"] / peak_tf
         cpu = None
