@@ -72,6 +72,7 @@ int get_tmap_bf16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* d
              rank > 3 ? box[3] : 0, ptr);
     return set_error(buf);
   }
+  if (g_tmaps.size() >= 8192) g_tmaps.clear();     // callers that pass ever-new buffers must not grow the cache without bound
   g_tmaps.emplace(key, m);
   *out = m;
   return 0;
