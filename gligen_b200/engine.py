@@ -487,8 +487,8 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # execution
     # ------------------------------------------------------------------------------------------
-    def _plan(self, Bt: int, N: int, nctx: int) -> Plan:
-        key = (Bt, N, nctx)
+    def _plan(self, Bt: int, N: int, nctx: int, slot: int = 0) -> Plan:
+        key = (Bt, N, nctx) if slot == 0 else (Bt, N, nctx, slot)       # one plan (and static-part cache) per batch chunk
         if key not in self.plans:
             self.plans[key] = self._build_plan(Bt, N, nctx)
         return self.plans[key]
@@ -564,15 +564,38 @@ class Engine:
                 out.append((t.data_ptr(), t._version, tuple(t.shape)))
         return tuple(out)
 
+    # glg_groupnorm handles at most 64 samples per call (one ticket word each); larger batches - BASELINE's keypoint
+    # sweep goes to 64 images = 128 CFG rows - run as chunks, each with its own plan, buffers and static-part cache.
+    MAX_ROWS = 64
+
+    @staticmethod
+    def _rows(t, lo, hi):
+        if t is None:
+            return None
+        if isinstance(t, dict):
+            return {k: v[lo:hi] for k, v in t.items()}
+        return t[lo:hi]
+
     @torch.no_grad()
     def forward(self, x, timesteps, context, grounding, inpainting_extra_input=None) -> torch.Tensor:
         """One UNet pass (UNetModel.forward semantics).  grounding=None -> null grounding tokens.
         Returns a NEW fp32 tensor [B, out_channels, H, W]."""
         assert self.loaded, "load_state_dict first"
         B = x.shape[0]
+        if B <= self.MAX_ROWS:
+            return self._forward_rows(x, timesteps, context, grounding, inpainting_extra_input, 0).clone()
+        outs = []
+        for slot, lo in enumerate(range(0, B, self.MAX_ROWS)):
+            hi = min(B, lo + self.MAX_ROWS)
+            outs.append(self._forward_rows(x[lo:hi], timesteps[lo:hi], context[lo:hi], self._rows(grounding, lo, hi),
+                                           self._rows(inpainting_extra_input, lo, hi), slot).clone())
+        return torch.cat(outs, 0)
+
+    def _forward_rows(self, x, timesteps, context, grounding, inpainting_extra_input, slot):
+        B = x.shape[0]
         N = self._n_objs(grounding) if grounding is not None else self._last_N
         self._last_N = N
-        P = self._plan(B, N, context.shape[1])
+        P = self._plan(B, N, context.shape[1], slot)
         P.inp["x"].copy_(x)
         P.inp["t"].copy_(timesteps)
         if self.cfg.inpaint_mode:
@@ -582,17 +605,31 @@ class Engine:
             P.inp["context"].copy_(context)
             self._stage_grounding(P, grounding, 0, B)
         self._execute(P, sig, (context, grounding))
-        return P.out.clone()
+        return P.out
 
     @torch.no_grad()
     def forward_cfg(self, x, timesteps, context, uc, grounding, inpainting_extra_input=None):
         """cond + uncond (null grounding, context = uc) as ONE 2B-row pass.  Returns (eps_cond, eps_uncond)
-        as views of the static output (valid until the next call)."""
+        as views of the static output (valid until the next call); batches above MAX_ROWS / 2 images run in chunks
+        and return new tensors."""
         assert self.loaded
+        B = x.shape[0]
+        per = self.MAX_ROWS // 2
+        if B <= per:
+            return self._forward_cfg_rows(x, timesteps, context, uc, grounding, inpainting_extra_input, 0)
+        conds, unconds = [], []
+        for slot, lo in enumerate(range(0, B, per)):
+            hi = min(B, lo + per)
+            c, u = self._forward_cfg_rows(x[lo:hi], timesteps[lo:hi], context[lo:hi], uc[lo:hi], self._rows(grounding, lo, hi),
+                                          self._rows(inpainting_extra_input, lo, hi), slot)
+            conds.append(c.clone()); unconds.append(u.clone())
+        return torch.cat(conds, 0), torch.cat(unconds, 0)
+
+    def _forward_cfg_rows(self, x, timesteps, context, uc, grounding, inpainting_extra_input, slot):
         B = x.shape[0]
         N = self._n_objs(grounding)
         self._last_N = N
-        P = self._plan(2 * B, N, context.shape[1])
+        P = self._plan(2 * B, N, context.shape[1], slot)
         P.inp["x"][:B].copy_(x); P.inp["x"][B:].copy_(x)
         P.inp["t"][:B].copy_(timesteps); P.inp["t"][B:].copy_(timesteps)
         if self.cfg.inpaint_mode:

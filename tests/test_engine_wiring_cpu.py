@@ -84,3 +84,28 @@ def test_first_conv_swap_is_in_place():
     from oracle import unet_oracle as UO
     ref = UO.unet_forward(cfg, sd2, inp["x"], ts, inp["context"], inp["grounding_input"])
     assert (e1 - ref).abs().max() < 5e-5 and (e0 - e1).abs().max() > 1e-3
+
+
+def test_large_batches_run_in_chunks(monkeypatch):
+    """Batches above Engine.MAX_ROWS rows (glg_groupnorm's per-call sample limit; BASELINE's keypoint sweep reaches
+    64 images = 128 CFG rows) run as chunks with their own plans: same result as one pass, static caches per chunk."""
+    cfg = NAMED_CONFIGS["tiny_inpaint"]
+    sd = synthetic_state_dict(cfg, 0)
+    inp = synth.make_inputs(cfg, 5, 4, seed=5)
+    mask = draw_masks_from_boxes(inp["batch"]["boxes"], cfg.image_size)
+    extra = torch.cat([inp["z0"] * mask, mask], 1)
+    ts = torch.tensor([801, 801, 801, 801, 801])
+    whole = Engine(cfg, RefOps())
+    whole.load_state_dict(sd)
+    e_ref = whole.forward(inp["x"], ts, inp["context"], inp["grounding_input"], extra)
+    c_ref, u_ref = (t.clone() for t in whole.forward_cfg(inp["x"], ts, inp["context"], inp["uc"], inp["grounding_input"], extra))
+    eng = Engine(cfg, RefOps())
+    eng.load_state_dict(sd)
+    monkeypatch.setattr(Engine, "MAX_ROWS", 4)
+    for rep in range(2):                                   # second round: every chunk hits its own static-part cache
+        e = eng.forward(inp["x"], ts, inp["context"], inp["grounding_input"], extra)          # chunks of 4 + 1 rows
+        c, u = eng.forward_cfg(inp["x"], ts, inp["context"], inp["uc"], inp["grounding_input"], extra)   # 2 + 2 + 1 images
+        assert e.shape == e_ref.shape and (e - e_ref).abs().max() < 2e-5
+        assert (c - c_ref).abs().max() < 2e-5 and (u - u_ref).abs().max() < 2e-5
+    assert len(eng.plans) == 2 + 2          # forward: 4-row and 1-row plans; cfg: 4-row plans in slots 0/1 share a shape key with
+                                            # forward's slot 0 only when the slot matches -> (4,.,.), (1,.,.,1), (4,.,.,1), (2,.,.,2)
