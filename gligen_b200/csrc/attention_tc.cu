@@ -66,8 +66,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 #define ATTN_EV(jj, slot) do { if (PROBE && ev_on && (jj) >= 8 && (jj) < 16) { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_)); p.probe[((jj) - 8) * 16 + (slot)] = t_; } } while (0)
 // ONES (d_head < DPAD): the MMA warp writes 1.0 into column d_head of every V tile, so O[:, d_head] accumulates the
 // row sum of the bf16 P the tensor core actually multiplied - the softmax loop then carries no FADD per score and no
-// running sum to rescale.  The softmax warps are issue-bound (profiles/: ~6 instructions per score, 4 warps per
-// sub-partition), so instructions removed from that loop are time removed from the kernel.
+// running sum to rescale.  (Measured at level 0: no change in time - profiles/r1_attention_pipeline.md shows the loop is
+// latency-, not issue-bound - kept because the row sum then matches the numerator's bf16 rounding exactly.)
 template <int DPAD, bool PROBE = false, bool ONES = false>   // head dim rounded up to a multiple of 16 (<= 128)
 __global__ void __launch_bounds__(320, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
