@@ -342,3 +342,96 @@ def flops_per_forward(cfg: UNetConfig, G: int, fuser_on: bool = True) -> float:
     gtok = G // n_mlp
     total += n_mlp * 2.0 * gtok * (din * cfg.tok_hidden + cfg.tok_hidden ** 2 + cfg.tok_hidden * cfg.tok_out_dim)
     return total
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY 8(f) rank 1 (next row, not on the hot path yet): the VAE decoder that turns the sampled
+# latent into pixels (reference ldm/models/autoencoder.py:40-44, ldm/modules/diffusionmodules/model.py:462-568).
+# Only the specification (state-dict keys / shapes, synthetic weights) lives here; the oracle is oracle/vae_oracle.py.
+# ------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class VAEDecoderConfig:
+    name: str = "sd14_vae"
+    ch: int = 128
+    ch_mult: Tuple[int, ...] = (1, 2, 4, 4)
+    num_res_blocks: int = 2
+    z_channels: int = 4
+    embed_dim: int = 4
+    out_ch: int = 3
+    latent_size: int = 64                 # decode(z) with z of shape [B, embed_dim, latent_size, latent_size]
+    scale_factor: float = 0.18215         # AutoencoderKL(scale_factor=...), configs/*: decode divides by it
+
+    @property
+    def image_size(self) -> int:
+        return self.latent_size * 2 ** (len(self.ch_mult) - 1)
+
+
+NAMED_VAE_CONFIGS = {
+    "sd14_vae": VAEDecoderConfig(),
+    "tiny_vae": VAEDecoderConfig(name="tiny_vae", ch=32, ch_mult=(1, 2), num_res_blocks=1, latent_size=8),
+}
+
+
+def vae_decoder_param_shapes(cfg: VAEDecoderConfig) -> "OrderedDict[str, tuple]":
+    """Keys / shapes of `post_quant_conv.*` and `decoder.*` in registration order (model.py:462-533)."""
+    p: "OrderedDict[str, tuple]" = OrderedDict()
+
+    def conv(prefix, cin, cout, k):
+        p[prefix + ".weight"] = (cout, cin, k, k)
+        p[prefix + ".bias"] = (cout,)
+
+    def norm(prefix, c):
+        p[prefix + ".weight"] = (c,)
+        p[prefix + ".bias"] = (c,)
+
+    def resblock(prefix, cin, cout):
+        norm(prefix + ".norm1", cin)
+        conv(prefix + ".conv1", cin, cout, 3)
+        norm(prefix + ".norm2", cout)
+        conv(prefix + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(prefix + ".nin_shortcut", cin, cout, 1)
+
+    conv("post_quant_conv", cfg.embed_dim, cfg.z_channels, 1)
+    nres = len(cfg.ch_mult)
+    block_in = cfg.ch * cfg.ch_mult[-1]
+    conv("decoder.conv_in", cfg.z_channels, block_in, 3)
+    resblock("decoder.mid.block_1", block_in, block_in)
+    norm("decoder.mid.attn_1.norm", block_in)
+    for nm in ("q", "k", "v", "proj_out"):
+        conv(f"decoder.mid.attn_1.{nm}", block_in, block_in, 1)
+    resblock("decoder.mid.block_2", block_in, block_in)
+    # nn.ModuleList `up` is built from the last level down but inserted at the front: state-dict order is level 0 first
+    per_level = {}
+    for i_level in reversed(range(nres)):
+        block_out = cfg.ch * cfg.ch_mult[i_level]
+        entries = []
+        for i_block in range(cfg.num_res_blocks + 1):
+            entries.append((f"decoder.up.{i_level}.block.{i_block}", block_in, block_out))
+            block_in = block_out
+        per_level[i_level] = (entries, block_in)
+    for i_level in range(nres):
+        entries, c = per_level[i_level]
+        for prefix, cin, cout in entries:
+            resblock(prefix, cin, cout)
+        if i_level != 0:
+            conv(f"decoder.up.{i_level}.upsample.conv", c, c, 3)
+    norm("decoder.norm_out", cfg.ch * cfg.ch_mult[0])
+    conv("decoder.conv_out", cfg.ch * cfg.ch_mult[0], cfg.out_ch, 3)
+    return p
+
+
+def synthetic_vae_state_dict(cfg: VAEDecoderConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Seeded fp32 CPU weights for the decoder half (same drawing rules as synthetic_state_dict)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = OrderedDict()
+    for key, shape in vae_decoder_param_shapes(cfg).items():
+        if key.endswith(".bias"):
+            t = torch.randn(shape, generator=g) * 0.05
+        elif len(shape) == 1:
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:
+            fan_in = shape[1] * shape[2] * shape[3]
+            t = torch.randn(shape, generator=g) * (fan_in ** -0.5)
+        sd[key] = t
+    return sd

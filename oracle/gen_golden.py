@@ -23,8 +23,26 @@ import torch
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
-sys.path.insert(0, REF)      # reference `ldm`, `grounding_input` win over the repo's drop-in package
+sys.path.insert(0, REF)      # reference `grounding_input`, `inpaint_mask_func`, ... win over the repo's drop-in modules
 sys.path.insert(1, REPO)
+
+
+def _mount_reference_package(name: str) -> None:
+    """The reference's `ldm` is a namespace package (no __init__.py) while the repo's drop-in `ldm` is a regular one,
+    which would win the import whatever the sys.path order: register `ldm` with the reference directory as its only
+    search location so that every `ldm.*` import below executes REFERENCE code."""
+    import importlib.machinery
+    import types
+    path = os.path.join(REF, name)
+    spec = importlib.machinery.ModuleSpec(name, None, is_package=True)
+    spec.submodule_search_locations = [path]
+    mod = types.ModuleType(name)
+    mod.__path__ = [path]
+    mod.__spec__ = spec
+    sys.modules[name] = mod
+
+
+_mount_reference_package("ldm")
 
 from gligen_b200.spec import NAMED_CONFIGS, synthetic_state_dict  # noqa: E402
 from gligen_b200 import synth  # noqa: E402
@@ -194,13 +212,49 @@ def scalar_anchors():
     print("anchors:", te[0, :2].tolist(), fe[0, :4].tolist(), float(sched["alphas_cumprod"][0]), float(al[0]), float(al[-1]), float(alp[-1]))
 
 
+def run_vae(name, B, seed=3, store_half=False):
+    """SURVEY 8(f) rank 1 (next row): pin oracle/vae_oracle.py against the reference AutoencoderKL.decode."""
+    from gligen_b200.spec import NAMED_VAE_CONFIGS, synthetic_vae_state_dict, vae_decoder_param_shapes
+    from oracle import vae_oracle as VO
+    from ldm.models.autoencoder import AutoencoderKL
+    assert "/root/reference" in sys.modules[AutoencoderKL.__module__].__file__
+    cfg = NAMED_VAE_CONFIGS[name]
+    dd = dict(double_z=True, z_channels=cfg.z_channels, resolution=cfg.image_size, in_channels=3, out_ch=cfg.out_ch, ch=cfg.ch,
+              ch_mult=list(cfg.ch_mult), num_res_blocks=cfg.num_res_blocks, attn_resolutions=[], dropout=0.0)
+    ref = AutoencoderKL(ddconfig=dd, embed_dim=cfg.embed_dim, scale_factor=cfg.scale_factor).eval()
+    ref_keys = [(k, tuple(v.shape)) for k, v in ref.state_dict().items() if k.startswith(("decoder.", "post_quant_conv."))]
+    mine = [(k, tuple(s)) for k, s in vae_decoder_param_shapes(cfg).items()]
+    assert sorted(ref_keys) == sorted(mine), "decoder state-dict keys / shapes differ from the reference"
+    assert [k for k, _ in ref_keys if k.startswith("decoder.")] == [k for k, _ in mine if k.startswith("decoder.")], "registration order differs"
+    sd = synthetic_vae_state_dict(cfg, 0)
+    missing, unexpected = ref.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith(("encoder.", "quant_conv.")) for k in missing)
+    g = torch.Generator().manual_seed(seed)
+    z = torch.randn(B, cfg.embed_dim, cfg.latent_size, cfg.latent_size, generator=g) * cfg.scale_factor * 4.0   # latents ~ 0.18215 * N(0, ~4^2)
+    t0 = time.time()
+    with torch.no_grad():
+        img = ref.decode(z)
+    t_ref = time.time() - t0
+    mine_img = VO.vae_decode(cfg, sd, z)
+    diff = (img - mine_img).abs().max().item()
+    print(f"{name}: reference decode {tuple(img.shape)} in {t_ref:.1f} s; max |oracle - reference| = {diff:.3e}; mean |img| = {img.abs().mean():.3f}")
+    assert diff <= 1e-4 * max(1.0, img.abs().max().item())
+    torch.save({"name": name, "B": B, "seed": seed, "z": z, "image": img.half() if store_half else img, "oracle_max_abs_diff": diff},
+               os.path.join(GOLD, f"{name}_B{B}.pt"))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
     ap.add_argument("--tiny", action="store_true")
+    ap.add_argument("--vae", action="store_true", help="only the VAE-decoder fixtures (next row, SURVEY 8f)")
     args = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     os.makedirs(GOLD, exist_ok=True)
+    if args.vae:
+        run_vae("tiny_vae", B=2)
+        run_vae("sd14_vae", B=1, store_half=True)
+        sys.exit(0)
     if args.tiny or not args.full:
         scalar_anchors()
         run_config("tiny", B=2, max_objs=6, plms_S=4, alpha_type=[0.5, 0, 0.5], ddim_S=2)

@@ -99,3 +99,22 @@ def test_fresh_init_invariants():
     e0 = UO.unet_forward(cfg, sd, inp["x"], ts, inp["context"], inp["grounding_input"], 0.0)
     e1 = UO.unet_forward(cfg, a0, inp["x"], ts, inp["context"], inp["grounding_input"], 1.0)
     assert torch.equal(e0, e1)
+
+
+@pytest.mark.parametrize("name,gold_file,tol", [("tiny_vae", "tiny_vae_B2.pt", 2e-5), ("sd14_vae", "sd14_vae_B1.pt", 2e-3)])
+def test_vae_decoder_oracle_matches_reference(name, gold_file, tol):
+    """SURVEY 8(f) rank 1, the row that comes next after the denoiser: oracle/vae_oracle.py against the image the
+    reference AutoencoderKL.decode produced for the same synthetic weights and latent (the full-size image is stored
+    in fp16, hence the looser bound; gen_golden measured an exact match)."""
+    from gligen_b200.spec import NAMED_VAE_CONFIGS, synthetic_vae_state_dict, vae_decoder_param_shapes
+    from oracle import vae_oracle as VO
+    gold = torch.load(os.path.join(GOLD, gold_file))
+    cfg = NAMED_VAE_CONFIGS[name]
+    assert gold["oracle_max_abs_diff"] <= 1e-4
+    if name == "sd14_vae":
+        shapes = vae_decoder_param_shapes(cfg)
+        assert len(shapes) == 140 and abs(sum(torch.Size(s).numel() for s in shapes.values()) - 49_490_199) == 0
+        assert cfg.image_size == 512
+    img = VO.vae_decode(cfg, synthetic_vae_state_dict(cfg, 0), gold["z"])
+    assert img.shape == gold["image"].shape
+    assert (img - gold["image"].float()).abs().max().item() <= tol * max(1.0, gold["image"].float().abs().max().item())
