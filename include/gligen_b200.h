@@ -101,6 +101,10 @@ int glg_gemm(const GlgGemmArgs* args, void* stream);
  * attention over [visual ; grounding] tokens with only the first Lq query rows kept, :241).
  * q/k/v are bf16 with independent row strides (elements) and batch strides so that packed QKV / KV
  * GEMM outputs are consumed in place.  d_head in {8,16,...,160}, multiple of 8.
+ * Kernel selection (csrc/attention_tc.cu, csrc/attention.cu): d_head <= 128 and Lk > 128 -> tcgen05/TMEM kernel (needs
+ * 16-byte aligned q/k/v/out and strides that are multiples of 8 elements); Lk <= 128 (the 77-token text context) ->
+ * K/V-resident mma.sync kernel; d_head > 128 -> streaming mma.sync kernel.  All three give the same result to bf16
+ * round-off (tests/test_kernels_gpu.py::test_attention runs them against each other's reference).
  */
 typedef struct GlgAttnArgs {
   const void* q; const void* k; const void* v; void* out;   /* bf16 */
