@@ -76,6 +76,7 @@ class Engine:
             self.emb_off[ly.prefix] = off
             off += ly.cout
         self.emb_total = off
+        self._last_N: Optional[int] = None      # grounding slots of the last grounded call (shape of the null input)
         self.n_streams = 2 if cfg.tokenizer == "text_image" else 1
         self.pos_k = _rup(cfg.tok_feat_dim + cfg.position_dim, 64)
 
@@ -551,17 +552,35 @@ class Engine:
             P.static_refs = refs
         self._run_part(P, fuser_on, False)
 
-    @staticmethod
-    def _sig(*tensors):
-        """Identity of caller tensors: same storage, same version counter, same shape -> same contents."""
+    def invalidate_static(self) -> None:
+        """Forget which inputs the timestep-invariant steps were last run for.  Tensor identity (below) cannot see
+        writes that bypass the version counter (`t.data.copy_()`, numpy / DLPack aliases, custom kernels), so callers
+        that reuse buffers call this between sampling runs; the samplers of this repo do it at the start of sample()."""
+        for P in self.plans.values():
+            P.static_sig = None
+            P.static_refs = None
+
+    _sig_serial = 0
+
+    @classmethod
+    def _sig(cls, *tensors):
+        """Identity of caller tensors: same storage, same version counter, same shape -> same contents.  Tensors
+        without a version counter (inference-mode tensors) get a fresh serial: never equal, always recomputed."""
+        def one(v):
+            try:
+                ver = v._version
+            except RuntimeError:
+                cls._sig_serial += 1
+                ver = ("unversioned", cls._sig_serial)
+            return (v.data_ptr(), ver, tuple(v.shape))
         out = []
         for t in tensors:
             if t is None:
                 out.append(None)
             elif isinstance(t, dict):
-                out.append(tuple((k, v.data_ptr(), v._version, tuple(v.shape)) for k, v in sorted(t.items())))
+                out.append(tuple((k,) + one(v) for k, v in sorted(t.items())))
             else:
-                out.append((t.data_ptr(), t._version, tuple(t.shape)))
+                out.append(one(t))
         return tuple(out)
 
     # glg_groupnorm handles at most 64 samples per call (one ticket word each); larger batches - BASELINE's keypoint
@@ -593,8 +612,13 @@ class Engine:
 
     def _forward_rows(self, x, timesteps, context, grounding, inpainting_extra_input, slot):
         B = x.shape[0]
-        N = self._n_objs(grounding) if grounding is not None else self._last_N
-        self._last_N = N
+        if grounding is not None:
+            N = self._last_N = self._n_objs(grounding)
+        elif self._last_N is None:
+            raise RuntimeError("forward(grounding=None) before any grounded call: the null grounding input has the shape "
+                               "of the last prepared one (GroundingNetInput.get_null_input asserts the same)")
+        else:
+            N = self._last_N
         P = self._plan(B, N, context.shape[1], slot)
         P.inp["x"].copy_(x)
         P.inp["t"].copy_(timesteps)

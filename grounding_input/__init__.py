@@ -3,6 +3,10 @@
 One table-driven base class; the three modules below only name their fields."""
 import torch
 
+from gligen_b200._overlay import extend as _extend
+
+__path__ = _extend(__path__, __name__)          # the reference's other adapters (hed / canny / depth / ...) stay importable
+
 
 class TableGroundingNetInput:
     #: (kwarg name, batch key)

@@ -47,6 +47,10 @@ class SamplerBase(object):
         self.register_buffer("ddim_alphas", al)
         self.register_buffer("ddim_alphas_prev", alp)
         self.register_buffer("ddim_sqrt_one_minus_alphas", np.sqrt(1. - al))
+        # host copies for the per-step scalars: indexing the device buffers would block the host on the whole UNet
+        # pass every step (float(tensor[i]) is a device-to-host sync)
+        self._alphas_host = [float(v) for v in np.asarray(al, dtype=np.float64)]
+        self._alphas_prev_host = [float(v) for v in np.asarray(alp, dtype=np.float64)]
 
     # ---- pieces shared by both loops -----------------------------------------------------------
     def _begin(self, shape, input):
@@ -54,6 +58,11 @@ class SamplerBase(object):
         if img is None:
             img = torch.randn(shape, device=self.device)          # RNG draw #1 (plms.py:72)
             input["x"] = img
+        # a new sample() call: the engine's cache of timestep-invariant work (PositionNet tokens, text K/V, grounding
+        # K/V) is only an intra-loop optimisation - never trust tensor identity across calls
+        inv = getattr(self.model, "invalidate_static", None)
+        if inv is not None:
+            inv()
         time_range = np.flip(self.ddim_timesteps)
         alphas = self.alpha_generator_func(len(time_range)) if self.alpha_generator_func is not None else None
         return img, time_range, alphas
@@ -92,7 +101,7 @@ class SamplerBase(object):
         _L.check(lib.glg_sampler_update(x.data_ptr(), e_c.data_ptr(), None if e_u is None else e_u.contiguous().data_ptr(),
                                         float(guidance_scale), o[0], o[1], o[2],
                                         float(coefs[0]), float(coefs[1]), float(coefs[2]), float(coefs[3]),
-                                        float(self.ddim_alphas[index]), float(self.ddim_alphas_prev[index]),
+                                        self._alphas_host[index], self._alphas_prev_host[index],
                                         None if e_out is None else e_out.data_ptr(), x_prev.data_ptr(), x.numel(), st),
                   "glg_sampler_update")
         return x_prev, e_out

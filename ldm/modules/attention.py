@@ -8,6 +8,7 @@ fused sm_100a kernels driven by gligen_b200.engine; the containers exist so that
   * `set_alpha_scale` (gligen_inference.py:24-28), which walks model.modules() and tests
     `type(module) == GatedSelfAttentionDense`, finds the fusers and sets `.scale` on them.
 """
+import torch
 import torch.nn as nn
 
 
@@ -27,6 +28,27 @@ class ParamNode(nn.Module):
     def forward(self, *args, **kwargs):
         raise RuntimeError(f"{type(self).__name__} is a parameter container; call UNetModel.forward(input) "
                            "(the whole denoiser runs inside the gligen_b200 engine)")
+
+
+class LinearAttention(nn.Module):
+    """Softmax-over-keys linear attention on feature maps (reference attention.py:80-99).  NOT on the denoiser's path
+    (no UNet config uses it); it lives here, as ordinary PyTorch, only because the reference's VAE module
+    `ldm/modules/diffusionmodules/model.py:9` imports this name from `ldm.modules.attention`, which this file replaces
+    in an overlay.  Parameter names (`to_qkv`, `to_out`) follow the reference so checkpoints load."""
+
+    def __init__(self, dim, heads=4, dim_head=32):
+        super().__init__()
+        self.heads = heads
+        inner = heads * dim_head
+        self.to_qkv = nn.Conv2d(dim, 3 * inner, kernel_size=1, bias=False)
+        self.to_out = nn.Conv2d(inner, dim, kernel_size=1)
+
+    def forward(self, x):
+        b, _, h, w = x.shape
+        q, k, v = self.to_qkv(x).view(b, 3, self.heads, -1, h * w).unbind(dim=1)      # each [b, heads, d, n]
+        ctx = torch.matmul(k.softmax(dim=-1), v.transpose(-1, -2))                   # [b, heads, d, e]
+        out = torch.matmul(ctx.transpose(-1, -2), q)                                 # [b, heads, e, n]
+        return self.to_out(out.reshape(b, -1, h, w))
 
 
 class SelfAttention(ParamNode):
@@ -72,3 +94,10 @@ class BasicTransformerBlock(ParamNode):
 
 class SpatialTransformer(ParamNode):
     pass
+
+
+# names this drop-in does not define resolve to the reference module of the same name when a reference checkout
+# follows this repo on sys.path (gligen_b200/_overlay.py)
+from gligen_b200._overlay import fallback as _fallback  # noqa: E402
+
+__getattr__ = _fallback(__name__, __file__)

@@ -119,12 +119,26 @@ class UNetModel(ParamNode):
     def load_state_dict(self, state_dict, strict=True, **kw):
         out = super().load_state_dict(state_dict, strict=strict, **kw)
         self._engine_stale = True
+        self._forget_first_conv_swap()
         return out
+
+    def _forget_first_conv_swap(self):
+        """New weights: the SD first conv is no longer what input_blocks[0][0] holds (the reference re-loads it on
+        every alpha == 0 step, openaimodel.py:400-413, so it never goes stale there)."""
+        self._sd_applied = False
+        if hasattr(self, "GLIGEN_first_conv_state_dict"):
+            del self.GLIGEN_first_conv_state_dict
+
+    def invalidate_static(self):
+        """Drop the engine's cache of timestep-invariant work (called by the samplers at the start of sample())."""
+        if self._engine is not None:
+            self._engine.invalidate_static()
 
     def _apply(self, fn, *a, **kw):
         out = super()._apply(fn, *a, **kw)              # .to(device) / .cuda(): re-pack on the next forward
         self._engine_stale = True
         self._engine = None
+        self._sd_applied = False
         return out
 
     def engine(self):
@@ -195,3 +209,10 @@ class UNetModel(ParamNode):
         self._sync_scales(eng)
         return eng.forward_cfg(input["x"], input["timesteps"], input["context"], uc, input["grounding_input"],
                                input.get("inpainting_extra_input") if self.inpaint_mode else None)
+
+
+# names this drop-in does not define resolve to the reference module of the same name when a reference checkout
+# follows this repo on sys.path (gligen_b200/_overlay.py)
+from gligen_b200._overlay import fallback as _fallback  # noqa: E402
+
+__getattr__ = _fallback(__name__, __file__)

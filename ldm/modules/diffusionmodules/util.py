@@ -81,3 +81,10 @@ def timestep_embedding(timesteps, dim, max_period=10000, repeat_only=False):
     if dim % 2:
         emb = torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1)
     return emb
+
+
+# names this drop-in does not define resolve to the reference module of the same name when a reference checkout
+# follows this repo on sys.path (gligen_b200/_overlay.py)
+from gligen_b200._overlay import fallback as _fallback  # noqa: E402
+
+__getattr__ = _fallback(__name__, __file__)

@@ -33,3 +33,10 @@ def count_params(model, verbose=False):
     if verbose:
         print(f"{model.__class__.__name__} has {n * 1.e-6:.2f} M params.")
     return n
+
+
+# names this drop-in does not define resolve to the reference module of the same name when a reference checkout
+# follows this repo on sys.path (gligen_b200/_overlay.py)
+from gligen_b200._overlay import fallback as _fallback  # noqa: E402
+
+__getattr__ = _fallback(__name__, __file__)

@@ -195,6 +195,65 @@ def run_config(name, B, max_objs, plms_S, alpha_type, ddim_S, n_valid=None, do_s
     print(f"   wrote {path} ({os.path.getsize(path)/1024:.0f} KiB)")
 
 
+@torch.no_grad()
+def run_plms50(name="sd14_box_text", B=1, max_objs=30, S=50, alpha_types=((1, 0, 0), (0.3, 0, 0.7)), twin_for=((0.3, 0, 0.7),)):
+    """The path the metric is quoted on: reference PLMSSampler.sample(S=50, guidance 7.5) at full size (102 UNet
+    forwards), for alpha_type [1,0,0] and the script default [0.3,0,0.7] (gligen_inference.py:389-390,475).
+    Stores the REFERENCE fp32 final latents; the oracle twin is re-checked on `twin_for`."""
+    cfg = NAMED_CONFIGS[name]
+    sd = synthetic_state_dict(cfg, seed=0)
+    gin = ref_grounding_input(cfg)
+    inp = synth.make_inputs(cfg, B, max_objs, seed=2)
+    grounding = gin.prepare(inp["batch"])
+    from ldm.models.diffusion.plms import PLMSSampler
+    from ldm.models.diffusion.ldm import LatentDiffusion
+    diffusion = LatentDiffusion(linear_start=0.00085, linear_end=0.012, timesteps=1000)
+    sched = SO.make_schedule()
+    shape = (B, cfg.in_channels, cfg.image_size, cfg.image_size)
+    sd_conv = torch.load(os.path.join(REF, "SD_input_conv_weight_bias.pth"))
+    out = {"cfg": name, "B": B, "max_objs": max_objs, "n_valid": None, "S": S, "guidance": 7.5, "runs": {}}
+    cwd = os.getcwd()
+    os.chdir(REF)
+    try:
+        for atype in alpha_types:
+            atype = list(atype)
+            m = ref_model(cfg)
+            m.load_state_dict(sd, strict=True)
+            m.grounding_tokenizer_input = gin
+            sampler = PLMSSampler(diffusion, m, alpha_generator_func=partial(SO.alpha_generator, type=atype), set_alpha_scale=set_alpha_scale)
+            input = dict(x=inp["x"].clone(), timesteps=None, context=inp["context"], grounding_input=grounding,
+                         inpainting_extra_input=None, grounding_extra_input=None)
+            torch.manual_seed(1234)
+            t1 = time.time()
+            ref = sampler.sample(S=S, shape=shape, input=input, uc=inp["uc"], guidance_scale=7.5)
+            print(f"   ref plms S={S} alpha={atype}: {time.time()-t1:.1f}s  latent std {ref.std():.3f} max {ref.abs().max():.3f}", flush=True)
+            del m, sampler
+            twin = None
+            if tuple(atype) in [tuple(t) for t in twin_for]:
+                state = {"scale": 1.0, "sd": dict(sd)}
+
+                def on_alpha(a):
+                    state["scale"] = a
+                    if a == 0:
+                        state["sd"]["input_blocks.0.0.weight"] = sd_conv["weight"]
+                        state["sd"]["input_blocks.0.0.bias"] = sd_conv["bias"]
+
+                def eps_fn(x, t, cond):
+                    gr = grounding if cond else UO.null_grounding(cfg, grounding)
+                    return UO.unet_forward(cfg, state["sd"], x, t, inp["context"] if cond else inp["uc"], gr, state["scale"], None)
+
+                torch.manual_seed(1234)
+                got = SO.plms_sample(eps_fn, S, shape, sched, x_T=inp["x"].clone(), use_cfg=True, guidance_scale=7.5,
+                                     alphas=SO.alpha_generator(S, atype), on_alpha=on_alpha)
+                check(f"plms S={S} alpha={atype} oracle twin", got, ref, 5e-4)
+                twin = (got - ref).abs().max().item()
+            out["runs"][str(atype)] = {"alpha_type": atype, "latent": ref.clone(), "oracle_twin_max_abs": twin}
+            torch.save(out, os.path.join(GOLD, f"{name}_B{B}_G{max_objs}_plms{S}.pt"))        # keep partial results
+    finally:
+        os.chdir(cwd)
+    print(f"   wrote {name}_B{B}_G{max_objs}_plms{S}.pt")
+
+
 def scalar_anchors():
     """Closed-form anchors from SURVEY 8c, checked against reference code and stored."""
     from ldm.modules.diffusionmodules.util import timestep_embedding, FourierEmbedder
@@ -248,12 +307,24 @@ if __name__ == "__main__":
     ap.add_argument("--full", action="store_true")
     ap.add_argument("--tiny", action="store_true")
     ap.add_argument("--vae", action="store_true", help="only the VAE-decoder fixtures (next row, SURVEY 8f)")
+    ap.add_argument("--configs345", action="store_true", help="full-size single forwards (+ short inpaint loops) for BASELINE configs 3, 4, 5")
+    ap.add_argument("--plms50", action="store_true", help="50-step PLMS + CFG final latents at full size (the path the metric is quoted on)")
     args = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     os.makedirs(GOLD, exist_ok=True)
     if args.vae:
         run_vae("tiny_vae", B=2)
         run_vae("sd14_vae", B=1, store_half=True)
+        sys.exit(0)
+    if args.configs345:
+        # BASELINE config 3 (box + text + image: 30 objects -> 60 grounding tokens), config 5 (keypoint: 8 x 17 = 136
+        # tokens), config 4 (inpainting: 9-channel first conv, scheduled sampling [0.3,0,0.7], per-step blend)
+        run_config("sd14_box_text_image", B=1, max_objs=30, plms_S=0, alpha_type=[1, 0, 0], ddim_S=0, do_sampling=False)
+        run_config("sd14_keypoint", B=1, max_objs=136, plms_S=0, alpha_type=[1, 0, 0], ddim_S=0, do_sampling=False)
+        run_config("sd14_inpaint_box_text", B=1, max_objs=30, plms_S=4, alpha_type=[0.3, 0, 0.7], ddim_S=2)
+    if args.plms50:
+        run_plms50()
+    if args.configs345 or args.plms50:
         sys.exit(0)
     if args.tiny or not args.full:
         scalar_anchors()
