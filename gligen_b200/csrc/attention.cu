@@ -296,8 +296,12 @@ static int launch_attn(const AttnKParams& p, int B, cudaStream_t st) {
 }  // namespace glg
 
 namespace glg {
-int attention_tc(const GlgAttnArgs* a, cudaStream_t st);   // attention_tc.cu: tcgen05 path for d_head <= 64
-int g_attn_mode = 0;          // 0 = auto, 1 = force the mma.sync kernel, 2 = force tcgen05 where it applies (test hooks)
+int attention_tc(const GlgAttnArgs* a, cudaStream_t st);         // attention_tc.cu: tcgen05 flash attention (streamed key tiles)
+int attention_short_tc(const GlgAttnArgs* a, cudaStream_t st);   // attention_short_tc.cu: tcgen05, all keys in one tile (Lk <= 128)
+int attention_tc2(const GlgAttnArgs* a, cudaStream_t st);        // attention_tc2.cu: tcgen05, key tiles dealt to two independent softmax warpgroups
+int g_attn_mode = 0;          // test hooks: 0 = auto, 1 = force the mma.sync kernel, 2 = force the streamed tcgen05 kernel,
+                              // 3 = force the short-key tcgen05 kernel, 4 = force the two-warpgroup tcgen05 kernel
+                              // (each "where it applies")
 }
 
 using namespace glg;
@@ -311,7 +315,15 @@ extern "C" int glg_attention(const GlgAttnArgs* a, void* stream) {
   if ((a->q_row | a->k_row | a->v_row | a->q_batch | a->k_batch | a->v_batch) % 8) return set_error("glg_attention: q/k/v strides must be multiples of 8 elements");
   if ((a->o_row | a->o_batch) % 2) return set_error("glg_attention: output strides must be even");
   if (((uintptr_t)a->q | (uintptr_t)a->k | (uintptr_t)a->v) & 15) return set_error("glg_attention: q/k/v must be 16-byte aligned");
-  if ((g_attn_mode == 0 && a->Lk > 128) || g_attn_mode == 2) {      // short key sets (text context): the K/V-resident mma.sync kernel below
+  if ((g_attn_mode == 0 && a->Lk <= 128) || g_attn_mode == 3) {     // short key sets (the 77-token text context)
+    const int rc = attention_short_tc(a, reinterpret_cast<cudaStream_t>(stream));
+    if (rc <= 0) return rc;
+  }
+  if ((g_attn_mode == 0 && a->Lk > 128) || g_attn_mode == 4) {      // d_head < 64 with a spare column (d_head = 40: the 64x64 level)
+    const int rc = attention_tc2(a, reinterpret_cast<cudaStream_t>(stream));
+    if (rc <= 0) return rc;
+  }
+  if ((g_attn_mode == 0 && a->Lk > 128) || g_attn_mode == 2 || g_attn_mode == 4) {
     const int rc = attention_tc(a, reinterpret_cast<cudaStream_t>(stream));
     if (rc <= 0) return rc;          // 0 = launched, -1 = error; 1 = not applicable -> mma.sync kernel below
   }

@@ -1,6 +1,6 @@
-// tcgen05 / TMEM flash attention for head dims <= 128 (d_head = 40 at the 64x64-latent level carries 88 % of the
-// attention FLOPs, d_head = 80 at 32x32 most of the rest).  Head dims above 64 use two 64-column
-// swizzle atoms per operand tile.
+// tcgen05 / TMEM flash attention for head dims <= 160 (d_head = 40 at the 64x64-latent level carries 88 % of the
+// attention FLOPs, d_head = 80 at 32x32 most of the rest, d_head = 160 at 16x16 / 8x8).  Head dims above 64
+// use two or three 64-column swizzle atoms per operand tile.
 //
 //   per CTA: one (batch, head, 128-query tile); key/value tiles of 64 keys stream through a TMA ring.
 //   warp 0 : TMA producer (Q once, then K_j / V_j tiles; 4-D tensor maps {d, head, row, batch},
@@ -11,9 +11,9 @@
 //   warps 2..9 : softmax  two threads per query row (32 of the tile's 64 keys each; partial row maxima are
 //            exchanged through smem): tcgen05.ld S_j -> running max (lazy rescale of O only when the max grows by
 //            > 2^8; only that rare path waits for P.V) -> exp2 -> P_j bf16 -> tcgen05.st.
-//   TMEM (256 columns): S[NSB] (64 fp32 each; P_j, 32 packed-bf16 columns, overwrites the first half of S_j once both
-//   warps of a row pair hold their scores in registers) | O (<= 128 fp32).  NSB = 3 for d_head <= 64 (QK^T runs two
-//   key tiles ahead), 2 above.  Two CTAs are resident per SM.
+//   TMEM (256 columns; 512 for d_head > 128): S[NSB] (64 fp32 each; P_j, 32 packed-bf16 columns, overwrites the first
+//   half of S_j once both warps of a row pair hold their scores in registers) | O (<= 160 fp32).  NSB = 3 for
+//   d_head <= 64 and > 128 (QK^T runs two key tiles ahead), 2 between.  Two CTAs are resident per SM (one for d_head > 128).
 //   When d_head is not a multiple of 16 the spare V column carries 1.0, so the row sums come out of the P.V MMA.
 //
 // Measured on B200 (profiles/r1_attention_pipeline.md): exp2 16/clk/SM, tcgen05.ld ~466 B/clk/SM, so a 128x128 score
@@ -42,11 +42,13 @@ constexpr int BM = 128, BN = 64;
 constexpr int QA_BYTES = BM * 64 * 2;       // one 64-column atom of Q: 16 KB
 constexpr int KVA_BYTES = BN * 64 * 2;      // one atom of K or V: 8 KB
 constexpr int XCH_BYTES = 2 * 2 * 128 * 4;  // [parity][column half][row] partial maxima / sums
-constexpr int TMEM_COLS = 256;
 constexpr int S_COL = 0;                    // S buffers first, then O; P_j lives in the first 32 columns of S_j
 template <int DPAD> struct Cfg {
   static constexpr int NATOM = (DPAD + 63) / 64;
-  static constexpr int STAGES = NATOM == 1 ? 4 : 2;
+  static constexpr int STAGES = NATOM == 1 ? 4 : (DPAD > 128 ? 3 : 2);     // >= NSB: QK^T_{j+NSB-1} is issued before P.V_j frees its stage
+  // d_head <= 128: S buffers + O fit 256 columns (two CTAs per SM); 144 / 160 take the whole TMEM (one CTA per SM)
+  static constexpr int TMEM_COLS = DPAD <= 128 ? 256 : 512;
+  static constexpr int NSB = (DPAD <= 64 || DPAD > 128) ? 3 : 2;
   static constexpr int Q_BYTES = NATOM * QA_BYTES;
   static constexpr int KV_BYTES = NATOM * KVA_BYTES;          // K (or V) of one stage
   static constexpr int SMEM_BYTES = Q_BYTES + STAGES * 2 * KV_BYTES + 1024 + 256 + XCH_BYTES;
@@ -68,8 +70,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // row sum of the bf16 P the tensor core actually multiplied - the softmax loop then carries no FADD per score and no
 // running sum to rescale.  (Measured at level 0: no change in time - profiles/r1_attention_pipeline.md shows the loop is
 // latency-, not issue-bound - kept because the row sum then matches the numerator's bf16 rounding exactly.)
-template <int DPAD, bool PROBE = false, bool ONES = false>   // head dim rounded up to a multiple of 16 (<= 128)
-__global__ void __launch_bounds__(320, 2)
+template <int DPAD, bool PROBE = false, bool ONES = false>   // head dim rounded up to a multiple of 16 (<= 160)
+__global__ void __launch_bounds__(320, DPAD <= 128 ? 2 : 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
   using namespace atc;
@@ -77,7 +79,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   constexpr int NATOM = C::NATOM, STAGES = C::STAGES;
   // S buffers: three when O leaves room (d_head <= 64), so QK^T runs TWO key tiles ahead of the softmax warps and
   // their s_full wait never sees the MMA issuer's per-tile latency (wake-up, P.V issue, commit, next QK^T issue).
-  constexpr int NSB = DPAD <= 64 ? 3 : 2;
+  constexpr int NSB = C::NSB;
+  constexpr int TMEM_COLS = C::TMEM_COLS;
   constexpr int O_COL = NSB * BN;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -358,7 +361,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (warp == 0) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, atc::TMEM_COLS);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -385,7 +388,7 @@ static int launch_attn_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CU
 
 // Returns 1 if this path does not apply (caller falls back to the mma.sync kernel), 0 on success, -1 on error.
 int attention_tc(const GlgAttnArgs* a, cudaStream_t st) {
-  if (a->d_head > 128) return 1;
+  if (a->d_head > 160) return 1;
   // tensor-map constraints: 16-byte aligned bases and strides; the output is written with 16-byte stores
   if ((a->d_head % 8) || (a->o_row % 8) || (a->o_batch % 8) || ((uintptr_t)a->out & 15)) return 1;
   CUtensorMap tq, tk, tv;
@@ -423,6 +426,8 @@ int attention_tc(const GlgAttnArgs* a, cudaStream_t st) {
     case 96: return launch_attn_tc<96>(tq, tk, tv, p, a->B, st);
     case 112: return launch_attn_tc<112>(tq, tk, tv, p, a->B, st);
     case 128: return launch_attn_tc<128>(tq, tk, tv, p, a->B, st);
+    case 144: return launch_attn_tc<144>(tq, tk, tv, p, a->B, st);
+    case 160: return launch_attn_tc<160>(tq, tk, tv, p, a->B, st);
   }
   return 1;
 }

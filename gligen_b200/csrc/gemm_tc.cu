@@ -18,10 +18,17 @@
 //                  are L2->SM bandwidth bound (a 128 x 256 tile needs ~96 B/clk/SM against ~42 available,
 //                  B300_MICROARCH "LTS throughput"); the paired tile halves that.
 //
+// B-resident mode (b_res): when a CTA's whole weight tile W[n_blk*BN .. +BN, 0..K) fits in shared memory next to a few
+// A stages (K*BN*2 bytes <= ~160 KB: the K = 320 / 640 projections), every CTA keeps ONE n-tile for its lifetime, loads
+// that weight tile once and streams only A tiles: L2 -> SM operand traffic per output tile drops from (128 + BN) to 128
+// rows per K step.  These short-K GEMMs are operand-delivery bound (ncu: tensor pipe 28 %, L2 -> SM at its ~60 B/clk/SM
+// limit), so this is worth up to (128 + BN) / 128 in time.
+//
 // conv_mode: the A operand is gathered by a 4-D tiled tensor map over the NHWC activation
 // (C, W, H, B); for tap (dy,dx) the box origin is shifted by (dx-1, dy-1) and TMA's out-of-bounds
 // zero fill implements the padding, so a 3x3 convolution is 9*Cin/64 K-steps of the same pipeline
-// with no im2col buffer.  A 128-row block is 128/W image rows (or 128/(H*W) whole images).
+// with no im2col buffer.  A 128-row block is 128/W image rows (or 128/(H*W) whole images, or a 128-pixel segment of one
+// row when W > 128).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -52,6 +59,14 @@ struct GemmKParams {
   // split-K: `splits` CTAs share one output tile, each reducing a contiguous range of K steps into its own fp32
   // slab ws[split][M][N]; splitk_reduce_kernel sums the slabs in a fixed order and applies the epilogue.
   int splits; float* ws;
+  int stages;                     // depth of the smem ring (runtime: B-resident mode trades stages for the weight tile)
+  int b_res;                      // 1: weights resident in smem, one n-tile per CTA for its lifetime
+  // epilogue data path through shared memory + TMA (see "epilogue data path" below)
+  int tma_out;                    // 0: per-thread global stores; 2 / 3: TMA stores with a 2-D / 3-D (batch-strided rows) tensor map
+  int tma_res;                    // 1: residual chunks arrive by TMA load into per-warp staging
+  unsigned epi_off;               // byte offset (from the tile base) of the epilogue staging area
+  long long stats_stride;         // stats_out / ln_stats are SLOT-major: element (slot, row) at [slot * stride + row]
+  long long ln_stride;
 };
 
 template <int BN, bool CTA2> struct GemmCfg {
@@ -60,13 +75,17 @@ template <int BN, bool CTA2> struct GemmCfg {
   static constexpr int BROWS = CTA2 ? BN / 2 : BN;                  // rows of W staged by one CTA
   static constexpr int B_BYTES = BROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (196 * 1024) / STAGE_BYTES > 8 ? 8 : (196 * 1024) / STAGE_BYTES;
+  static constexpr int MAX_STAGES = 12;
+  static constexpr int STAGES = (196 * 1024) / STAGE_BYTES > 8 ? 8 : (196 * 1024) / STAGE_BYTES;     // streaming mode
   // accumulator stages in TMEM: short-K tiles are bound by the MMA <-> epilogue hand-off latency, so use as many
   // stages as the 512 columns allow (BN=256: 2, 160: 3, <=128: 4)
   static constexpr int ACC = (512 / BN) > 4 ? 4 : (512 / BN);
   static constexpr int TMEM_COLS = (ACC * BN <= 128) ? 128 : (ACC * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static_assert(8 * (2 * STAGES + 2 * ACC) + 8 <= 256, "barrier area");
+  static constexpr int BAR_BYTES = 1024;                             // barriers live in FRONT of the tiles (runtime stage count)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + BAR_BYTES;
+  static constexpr int SMEM_MAX = 227 * 1024;                        // B-resident mode takes the whole SM
+  static constexpr int TILE_BYTES_MAX = SMEM_MAX - 1024 - BAR_BYTES;
+  static_assert(8 * (2 * MAX_STAGES + 2 * ACC + 1) + 8 <= BAR_BYTES, "barrier area");
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment of the next A stage");
 };
 
@@ -124,6 +143,38 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
+// ---- epilogue data path --------------------------------------------------------------------------------------
+// In the epilogue a thread owns one accumulator ROW (TMEM lane).  Writing that row's 64-byte chunks straight to global
+// memory makes every warp-level store touch 32 different 128-byte lines: the LSU replays it ~32 x 2 cycles, and the
+// same for the residual reads and the LayerNorm partials.  For the short-K projections (K = 320: 1600 MMA cycles per
+// tile) those replays - ~6500 cycles per 128 x 160 tile - were the whole kernel time (measured: the same 22 us with or
+// without the weight tile resident in smem).  So every per-row global access of the epilogue goes through shared
+// memory and the TMA instead: a warp stages its [32 rows x 32 columns] bf16 chunk in a 64B-swizzled 2 KB buffer
+// (conflict-free 16-byte st.shared) and one elected lane issues cp.async.bulk.tensor stores; residual chunks arrive
+// the same way in the other direction (per-warp mbarrier); the LayerNorm partial sums are kept SLOT-major
+// ([slot][row]) so that consecutive lanes touch consecutive addresses.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// 64B swizzle (CU_TENSOR_MAP_SWIZZLE_64B): 16-byte chunk index ^= address bits [7,9); rows of 64 bytes, 512-byte aligned buffer
+__device__ __forceinline__ uint32_t sw64_addr(uint32_t buf, int row, int piece) {
+  return buf + (uint32_t)row * 64u + ((uint32_t)(piece ^ ((row >> 1) & 3)) << 4);
+}
+struct EpiWarp {              // per-warp epilogue staging state
+  uint32_t out_stage;         // 2 x 2 KB
+  uint32_t res_stage;         // 2 x 2 KB
+  uint32_t res_bar;           // 2 mbarriers
+  uint32_t res_phase;         // bit i: phase of res_bar[i]
+  int out_buf, res_buf;       // next buffer to use
+};
+
 // 256-bit global accesses (sm_100: STG/LDG.256): a thread's 64-byte bf16 row chunk leaves as two full 32-byte
 // sectors instead of four half-sector writes (which doubled the L1->L2 crossbar write traffic).
 __device__ __forceinline__ void st_global_256(void* p, const uint32_t (&r)[8]) {
@@ -168,10 +219,50 @@ __device__ __forceinline__ void load_res_chunk(const bf16* src, uint4 (&r)[4], b
 
 // ---- epilogue of one 128-row x BN accumulator for the calling warp (lane quarter q, chunk half `half`) -----
 // res_pre: the first residual chunk, fetched before the accumulator became ready (latency hidden behind the MMA).
+// stage one packed [32 rows x 32 cols] chunk of this warp and hand it to the TMA (row0 = first row of the warp's slab)
+__device__ __forceinline__ void epi_tma_store(const GemmKParams& p, const CUtensorMap* tmOut, EpiWarp& ew, const uint32_t (&pk)[16],
+                                              int lane, int row0, int col0) {
+  if (lane == 0) tma_store_wait_read<1>();            // the buffer written two chunks ago has been read out
+  __syncwarp();
+  const uint32_t buf = ew.out_stage + (uint32_t)ew.out_buf * 2048u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw64_addr(buf, lane, j)), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
+                 "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
+  fence_proxy_async();                                // generic-proxy writes -> visible to the TMA (async proxy)
+  __syncwarp();
+  if (lane == 0) {
+    if (p.tma_out == 3) tma_store_3d(tmOut, buf, col0, row0 % p.orpb, row0 / p.orpb);
+    else tma_store_2d(tmOut, buf, col0, row0);
+    tma_store_commit();
+  }
+  ew.out_buf ^= 1;
+}
+// residual chunk (col0) of this warp's slab -> staging buffer ew.res_buf (arrives on its mbarrier)
+__device__ __forceinline__ void epi_res_issue(const CUtensorMap* tmRes, EpiWarp& ew, int lane, int row0, int col0) {
+  if (lane == 0) {
+    const uint32_t bar = ew.res_bar + 8u * ew.res_buf;
+    mbar_arrive_expect_tx(bar, 2048);
+    tma_load_2d(ew.res_stage + (uint32_t)ew.res_buf * 2048u, tmRes, bar, col0, row0);
+  }
+  ew.res_buf ^= 1;
+}
+__device__ __forceinline__ void epi_res_take(EpiWarp& ew, int buf, int lane, uint4 (&r)[4]) {
+  mbar_wait(ew.res_bar + 8u * buf, (ew.res_phase >> buf) & 1u);
+  ew.res_phase ^= 1u << buf;
+  const uint32_t b = ew.res_stage + (uint32_t)buf * 2048u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[j].x), "=r"(r[j].y), "=r"(r[j].z), "=r"(r[j].w) : "r"(sw64_addr(b, lane, j)) : "memory");
+  __syncwarp();                                       // all lanes hold their rows: the buffer may be refilled
+}
+
 template <int BN, bool GEGLU>
 __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t taddr, int row, int n_blk, int half, float gate,
-                                              float ln_mu, float ln_rstd, uint4 (&res_pre)[4]) {
+                                              float ln_mu, float ln_rstd, uint4 (&res_pre)[4],
+                                              const CUtensorMap* tmOut, const CUtensorMap* tmRes, EpiWarp& ew, int lane) {
   const bool row_ok = row < p.M;
+  const int row0 = row - lane;                        // first row of this warp's 32-row slab
   const size_t out_off = p.orpb ? (size_t)(row / p.orpb) * p.obs + (size_t)(row % p.orpb) * p.ldc : (size_t)row * p.ldc;
   if constexpr (GEGLU) {
     constexpr int HALF = BN / 2;
@@ -211,24 +302,38 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
         v[j + 2] = (__uint_as_float(rx[j + 2]) + tx.z) * gelu_erf_f(__uint_as_float(rg[j + 2]) + tg.z);
         v[j + 3] = (__uint_as_float(rx[j + 3]) + tx.w) * gelu_erf_f(__uint_as_float(rg[j + 3]) + tg.w);
       }
-      if (row_ok) epi_store_bf16(reinterpret_cast<bf16*>(p.out) + out_off + (size_t)n_blk * HALF + c * 32, v, p.wide != 0);
+      if (p.tma_out) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        epi_tma_store(p, tmOut, ew, pk, lane, row0, n_blk * HALF + c * 32);
+      } else if (row_ok) {
+        epi_store_bf16(reinterpret_cast<bf16*>(p.out) + out_off + (size_t)n_blk * HALF + c * 32, v, p.wide != 0);
+      }
     }
   } else {
     const float* rb = (p.rowbias && row_ok) ? p.rowbias + (size_t)(row / p.rows_per_batch) * p.ld_rowbias : nullptr;
     constexpr int NCH = BN / 32;
     const int c_begin = half ? (NCH + 1) / 2 : 0, c_end = half ? NCH : (NCH + 1) / 2;
-    const bool has_res = p.residual != nullptr && row_ok;
-    const bf16* res_row = has_res ? p.residual + (size_t)row * p.ldr + (size_t)n_blk * BN : nullptr;
+    const bool has_res = p.residual != nullptr && (row_ok || p.tma_res);
+    const bf16* res_row = (has_res && !p.tma_res) ? p.residual + (size_t)row * p.ldr + (size_t)n_blk * BN : nullptr;
     uint32_t r_next[32];
     if (c_begin < c_end) tmem_ld32(taddr + c_begin * 32, r_next);
 #pragma unroll 1
     for (int c = c_begin; c < c_end; ++c) {
       uint32_t r[32];
       uint4 res_cur[4];
+      if (p.tma_res) {
+        // this chunk's residual was requested one chunk (or one tile prologue) ago; request the next one right away
+        const int buf = ew.res_buf ^ 1;               // the buffer issued last
+        epi_res_take(ew, buf, lane, res_cur);
+        if (c + 1 < c_end) epi_res_issue(tmRes, ew, lane, row0, n_blk * BN + (c + 1) * 32);
+      } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) res_cur[i] = res_pre[i];
-      if (has_res && c + 1 < c_end)             // next chunk's residual: in flight while this chunk is processed
-        load_res_chunk(res_row + (c + 1) * 32, res_pre, p.wide != 0);
+        for (int i = 0; i < 4; ++i) res_cur[i] = res_pre[i];
+        if (has_res && c + 1 < c_end)             // next chunk's residual: in flight while this chunk is processed
+          load_res_chunk(res_row + (c + 1) * 32, res_pre, p.wide != 0);
+      }
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) r[j] = r_next[j];
@@ -267,7 +372,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= gate;
       }
-      if (row_ok) {
+      if (row_ok || p.tma_out) {
         if (has_res) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -286,10 +391,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-          if (p.stats_out) {
+          if (p.stats_out && row_ok) {
             // statistics of the values AS STORED (bf16-rounded): exactly what the consumer GEMM reads.  One partial
             // per 32-column chunk, slot = global chunk index: independent of the tile shape, so the consumer's
-            // fixed-order sum is bit-identical whatever kernel variant produced the rows.
+            // fixed-order sum is bit-identical whatever kernel variant produced the rows.  SLOT-major: the 32 lanes
+            // (consecutive rows) write 256 consecutive bytes.
             float st_sum = 0.f, st_sq = 0.f;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -297,9 +403,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
               st_sum += f.x + f.y;
               st_sq = fmaf(f.x, f.x, fmaf(f.y, f.y, st_sq));
             }
-            reinterpret_cast<float2*>(p.stats_out)[(size_t)row * p.stats_slots + (n0 >> 5)] = make_float2(st_sum, st_sq);
+            reinterpret_cast<float2*>(p.stats_out)[(size_t)(n0 >> 5) * p.stats_stride + row] = make_float2(st_sum, st_sq);
           }
-          epi_store_packed(reinterpret_cast<bf16*>(p.out) + out_off + n0, pk, p.wide != 0);
+          if (p.tma_out) epi_tma_store(p, tmOut, ew, pk, lane, row0, n0);
+          else epi_store_packed(reinterpret_cast<bf16*>(p.out) + out_off + n0, pk, p.wide != 0);
         }
       }
     }
@@ -375,19 +482,26 @@ __global__ void splitk_reduce_kernel(const GemmKParams p) {
 
 template <int BN, bool GEGLU, bool CTA2>
 __global__ void __launch_bounds__(320, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const GemmKParams p) {
   using Cfg = GemmCfg<BN, CTA2>;
-  constexpr int STAGES = Cfg::STAGES;
+  constexpr int MAXST = Cfg::MAX_STAGES;
   constexpr int ROWS_PER_TILE = CTA2 ? 256 : 128;
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t base = bar_base + Cfg::BAR_BYTES;                   // tiles (1024-byte aligned)
+  const int STAGES = p.stages;
+  const bool bres = !CTA2 && p.b_res != 0;
+  const uint32_t stage_bytes = bres ? (uint32_t)Cfg::A_BYTES : (uint32_t)Cfg::STAGE_BYTES;
+  const uint32_t bres_base = base + (uint32_t)STAGES * Cfg::A_BYTES;  // resident weight tile: num_kb x [BN rows x 128 B]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAXST + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAXST + a); };
   constexpr int ACC = Cfg::ACC;
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + ACC + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * ACC);
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAXST + ACC + a); };
+  const uint32_t bfull_bar = bar_base + 8u * (2 * MAXST + 2 * ACC);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAXST + 2 * ACC + 1);
+  const uint32_t res_bars = bar_base + 8u * (2 * MAXST + 2 * ACC + 2);      // 8 epilogue warps x 2
 
   pdl_trigger();          // the next kernel may start its prologue while this one runs (it waits before touching memory)
   const int warp = threadIdx.x >> 5;
@@ -398,12 +512,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(bfull_bar, 1);
+    for (int i = 0; i < 16; ++i) mbar_init(res_bars + 8u * i, 1);
     // accumulator drained: one arrive per epilogue warp, from both CTAs of a pair (on the leader's barrier)
     for (int a = 0; a < ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), CTA2 ? 16 : 8); }
     fence_barrier_init();
   }
   if (warp == 0) {
-    if (lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+      if (p.tma_out) tma_prefetch_desc(&tmOut);
+      if (p.tma_res) tma_prefetch_desc(&tmRes);
+    }
     __syncwarp();
     if constexpr (CTA2) { tmem_alloc2(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish2(); }
     else { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
@@ -416,44 +536,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   pdl_wait();             // everything above overlapped the previous kernel's tail; global data is touched only below
 
   const int total_work = p.tiles_m * p.tiles_n * p.splits;
+  // work item `it` of this CTA (pair) -> (m_blk, n_blk, split).  Streaming: round robin over all (tile, split) items.
+  // B-resident: the CTA keeps n-tile unit % tiles_n and walks m-blocks (the grid is a whole multiple of tiles_n).
+  const int per_n = bres ? num_units / p.tiles_n : 1;
+  auto get_work = [&](int it, int& tile, int& split, int& m_blk, int& n_blk) -> bool {
+    if (bres) {
+      n_blk = unit % p.tiles_n;
+      m_blk = unit / p.tiles_n + it * per_n;
+      split = 0;
+      tile = m_blk * p.tiles_n + n_blk;
+      return m_blk < p.tiles_m;
+    }
+    const int work = unit + it * num_units;
+    if (work >= total_work) return false;
+    tile = work / p.splits; split = work - tile * p.splits;
+    m_blk = tile / p.tiles_n; n_blk = tile - m_blk * p.tiles_n;
+    return true;
+  };
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA loads its own 128 rows of A and its share of B) ==========
     // whole warp walks the loop, one elected lane issues (see elect_one())
     const bool leader = elect_one();
     int stage = 0; uint32_t phase = 0;
-    for (int work = unit; work < total_work; work += num_units) {
-      const int tile = work / p.splits, split = work - tile * p.splits;
+    if (bres && leader) {
+      // the CTA's weight tile, once: num_kb boxes of [BN rows x 64 columns] on one barrier
+      const int brow = (unit % p.tiles_n) * BN;
+      mbar_arrive_expect_tx(bfull_bar, (uint32_t)p.num_kb * Cfg::B_BYTES);
+      for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(bres_base + (uint32_t)kb * Cfg::B_BYTES, &tmB, bfull_bar, kb * 64, brow);
+    }
+    int tile, split, m_blk, n_blk;
+    for (int it = 0; get_work(it, tile, split, m_blk, n_blk); ++it) {
       const int kb_lo = (split * p.num_kb) / p.splits, kb_n = ((split + 1) * p.num_kb) / p.splits - kb_lo;
-      const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
       const int row0 = m_blk * ROWS_PER_TILE + (int)rank * 128;
-      int b0 = 0, y0 = 0;
+      int b0 = 0, y0 = 0, x0 = 0;
       if (p.conv) {
         b0 = row0 / p.HW;
         y0 = (row0 - b0 * p.HW) / p.Wd;
+        x0 = row0 - b0 * p.HW - y0 * p.Wd;          // non-zero only for images wider than a tile (W > 128: part of one row)
       }
       const int brow0 = n_blk * BN + (int)rank * Cfg::BROWS;
       // K steps are visited in a per-tile rotated order: tiles running at the same time would otherwise request
       // the very same weight (and activation) lines from L2 in lockstep; the rotation spreads them over slices.
-      // (fp32 accumulation order depends only on the tile index -> results stay reproducible.)
-      int kb = kb_lo + (int)(((unsigned)tile * 3u) % (unsigned)kb_n);
-      for (int it = 0; it < kb_n; ++it, kb = (kb + 1 == kb_lo + kb_n) ? kb_lo : kb + 1) {
+      // (fp32 accumulation order depends only on the tile index -> results stay reproducible.)  B-resident tiles
+      // fetch no weights per tile and walk K in order (the MMA warp indexes the resident tile by K step).
+      int kb = bres ? kb_lo : kb_lo + (int)(((unsigned)tile * 3u) % (unsigned)kb_n);
+      for (int it2 = 0; it2 < kb_n; ++it2, kb = (kb + 1 == kb_lo + kb_n) ? kb_lo : kb + 1) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t a_dst = base + stage * Cfg::STAGE_BYTES;
+        const uint32_t a_dst = base + stage * stage_bytes;
         const uint32_t b_dst = a_dst + Cfg::A_BYTES;
         if (leader) {
         // the leader CTA's barrier collects the bytes of both CTAs
-        if (!CTA2) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+        if (bres) mbar_arrive_expect_tx(full_bar(stage), Cfg::A_BYTES);
+        else if (!CTA2) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
         else if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
         if (p.conv) {
           const int tap = kb / p.kb_per_tap;
           const int cb = kb - tap * p.kb_per_tap;
           const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
           if constexpr (CTA2) {
-            tma_load_4d_2sm(a_dst, &tmA, full_bar(stage), cb * 64, dx, y0 + dy, b0);
+            tma_load_4d_2sm(a_dst, &tmA, full_bar(stage), cb * 64, x0 + dx, y0 + dy, b0);
             tma_load_2d_2sm(b_dst, &tmB, full_bar(stage), cb * 64, tap * p.N + brow0);
           } else {
-            tma_load_4d(a_dst, &tmA, full_bar(stage), cb * 64, dx, y0 + dy, b0);
+            tma_load_4d(a_dst, &tmA, full_bar(stage), cb * 64, x0 + dx, y0 + dy, b0);
             tma_load_2d(b_dst, &tmB, full_bar(stage), cb * 64, tap * p.N + brow0);
           }
         } else {
@@ -462,7 +607,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_2d_2sm(b_dst, &tmB, full_bar(stage), kb * 64, brow0);
           } else {
             tma_load_2d(a_dst, &tmA, full_bar(stage), kb * 64, row0);
-            tma_load_2d(b_dst, &tmB, full_bar(stage), kb * 64, brow0);
+            if (!bres) tma_load_2d(b_dst, &tmB, full_bar(stage), kb * 64, brow0);
           }
         }
         }
@@ -475,8 +620,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool leader = elect_one();
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int work = unit; work < total_work; work += num_units) {
-      const int split = work % p.splits;
+    if (bres) { mbar_wait(bfull_bar, 0); tc_fence_after(); }
+    int tile, split, m_blk, n_blk;
+    for (int it = 0; get_work(it, tile, split, m_blk, n_blk); ++it) {
       const int kb_n = ((split + 1) * p.num_kb) / p.splits - (split * p.num_kb) / p.splits;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
@@ -484,9 +630,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = 0; kb < kb_n; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t a_addr = base + stage * Cfg::STAGE_BYTES;
+        const uint32_t a_addr = base + stage * stage_bytes;
         const uint64_t adesc = umma_desc_kmajor_sw128(a_addr);
-        const uint64_t bdesc = umma_desc_kmajor_sw128(a_addr + Cfg::A_BYTES);
+        const uint64_t bdesc = umma_desc_kmajor_sw128(bres ? bres_base + (uint32_t)kb * Cfg::B_BYTES : a_addr + Cfg::A_BYTES);
         if (leader) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {   // 4 x K=16 inside one 64-wide (128 B) swizzle atom: +32 B per step
@@ -509,31 +655,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0; uint32_t acc_phase = 0;
     const float gate = p.gate ? __ldg(p.gate) : 1.0f;
     const uint32_t tempty_leader0 = CTA2 ? mapa_cluster(tempty_bar(0), 0) : tempty_bar(0);   // consecutive stages: +8 bytes
-    for (int work = unit; work < total_work; work += num_units) {
-      const int tile = work / p.splits, split = work - tile * p.splits;
-      const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
+    EpiWarp ew;
+    ew.out_stage = base + p.epi_off + (uint32_t)(warp - 2) * 4096u;
+    ew.res_stage = base + p.epi_off + 32768u + (uint32_t)(warp - 2) * 4096u;
+    ew.res_bar = res_bars + 16u * (uint32_t)(warp - 2);
+    ew.res_phase = 0; ew.out_buf = 0; ew.res_buf = 0;
+    int tile, split, m_blk, n_blk;
+    for (int it = 0; get_work(it, tile, split, m_blk, n_blk); ++it) {
       const int row = m_blk * ROWS_PER_TILE + (int)rank * 128 + q * 32 + lane;
       // ---- prefetch what does not depend on the accumulator: LayerNorm statistics and the first residual chunk
       float ln_mu = 0.f, ln_rstd = 1.f;
       if (p.ln_stats && row < p.M) {
-        const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + (size_t)row * p.ln_slots;
+        const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + row;          // slot-major: coalesced across the warp
         float s1 = 0.f, s2 = 0.f;
-        for (int i = 0; i < p.ln_slots; ++i) { const float2 t = __ldg(sp + i); s1 += t.x; s2 += t.y; }   // fixed order
+        for (int i = 0; i < p.ln_slots; ++i) { const float2 t = __ldg(sp + (size_t)i * p.ln_stride); s1 += t.x; s2 += t.y; }   // fixed order
         ln_mu = s1 * p.inv_k;
         ln_rstd = rsqrtf(fmaxf(s2 * p.inv_k - ln_mu * ln_mu, 0.f) + p.ln_eps);
       }
       uint4 res_pre[4] = {};
-      if (!GEGLU && p.residual && row < p.M) {
+      if (!GEGLU && p.residual && p.splits == 1) {
         constexpr int NCH = BN / 32;
         const int c_begin = half ? (NCH + 1) / 2 : 0, c_end = half ? NCH : (NCH + 1) / 2;
-        if (c_begin < c_end)
-          load_res_chunk(p.residual + (size_t)row * p.ldr + (size_t)n_blk * BN + c_begin * 32, res_pre, p.wide != 0);
+        if (c_begin < c_end) {
+          if (p.tma_res) epi_res_issue(&tmRes, ew, lane, row - lane, n_blk * BN + c_begin * 32);
+          else if (row < p.M) load_res_chunk(p.residual + (size_t)row * p.ldr + (size_t)n_blk * BN + c_begin * 32, res_pre, p.wide != 0);
+        }
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       if (p.splits > 1) epilogue_partial<BN>(p, taddr, row, n_blk, half, split);
-      else epilogue_tile<BN, GEGLU>(p, taddr, row, n_blk, half, gate, ln_mu, ln_rstd, res_pre);
+      else epilogue_tile<BN, GEGLU>(p, taddr, row, n_blk, half, gate, ln_mu, ln_rstd, res_pre, &tmOut, &tmRes, ew, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -542,6 +694,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (++acc == ACC) { acc = 0; acc_phase ^= 1u; }
     }
+    if (p.tma_out && lane == 0) tma_store_wait_read<0>();     // the staging buffers must outlive the TMA's reads
   }
 
   tc_fence_before();
@@ -557,24 +710,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // launch
 // ------------------------------------------------------------------------------------------------
 template <int BN, bool GEGLU, bool CTA2>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& p, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tres, const GemmKParams& p,
+                       size_t smem, cudaStream_t st) {
   using Cfg = GemmCfg<BN, CTA2>;
   static bool attr_set = false;
   auto kern = gemm_tc_kernel<BN, GEGLU, CTA2>;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_MAX);
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(gemm): ") + cudaGetErrorString(e));
     attr_set = true;
   }
   const int tiles = p.tiles_m * p.tiles_n * p.splits;
   int grid;
-  if (CTA2) {
+  if (p.b_res) {
+    grid = (num_sms() / p.tiles_n) * p.tiles_n;          // one n-tile per CTA for its lifetime
+  } else if (CTA2) {
     const int pairs = num_sms() / 2;
     grid = 2 * (tiles < pairs ? tiles : pairs);
   } else {
     grid = tiles < num_sms() ? tiles : num_sms();
   }
-  cudaError_t e = launch_k(kern, dim3(grid), dim3(320), Cfg::SMEM_BYTES, st, CTA2 ? 2 : 1, ta, tb, p);
+  cudaError_t e = launch_k(kern, dim3(grid), dim3(320), smem, st, CTA2 ? 2 : 1, ta, tb, tout, tres, p);
   count_launch();
   if (e != cudaSuccess) return set_error(std::string("gemm launch: ") + cudaGetErrorString(e));
   if (check_launch("gemm launch")) return -1;
@@ -593,20 +749,35 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmK
 int g_force_bn = 0;     // test hooks (glg_debug_force_bn / glg_debug_gemm_cta2 / glg_debug_splitk)
 int g_splitk_mode = 0;  // 0 = heuristic, 1 = never, 2 = split whenever legal
 int g_cta2_mode = -1;   // 0 = heuristic, 1 = never pair, 2 = pair whenever legal; -1 = read GLG_GEMM_CTA2 (default 0)
+int g_epi_mode = -1;    // test hook: -1 = GLG_GEMM_EPI / default, 0 = per-thread epilogue accesses, 1 = TMA epilogue
+int g_bres_mode = -1;   // B-resident tiles: 0 = heuristic, 1 = never, 2 = whenever legal; -1 = read GLG_GEMM_BRES (default 0)
+
+// A stages left beside a resident [BN x K] weight tile (0: does not fit)
+static int bres_stages(int bn, int num_kb) {
+  const long long tile_max = 227 * 1024 - 1024 - 1024;
+  const long long left = tile_max - (long long)num_kb * bn * 128;
+  if (left < 3 * 16384) return 0;
+  const int st = (int)(left / 16384);
+  return st > 12 ? 12 : st;
+}
 
 // Tile / split choice by a small time model (cycles):
 //   per 64-wide K step an SM needs max(MMA = 2*BN, operand bytes / ~42 B/clk of L2->SM bandwidth) cycles (a pair
 //   stages 128 + BN/2 operand rows per SM instead of 128 + BN); a CTA pays ~3000 cycles of fixed cost per work item;
 //   split-K adds a reduce pass over splits * M * N fp32.  The least estimated time wins.
 static void pick_tile(int M, int N, int num_kb, bool geglu, bool conv, int max_splits, long long ws_bytes,
-                      int* bn_out, int* cta2_out, int* splits_out) {
+                      int* bn_out, int* cta2_out, int* splits_out, int* bres_out) {
   if (g_cta2_mode < 0) {
     const char* e = getenv("GLG_GEMM_CTA2");
     g_cta2_mode = e ? atoi(e) : 0;
   }
+  if (g_bres_mode < 0) {
+    const char* e = getenv("GLG_GEMM_BRES");
+    g_bres_mode = e ? atoi(e) : 1;      // measured (profiles/r2): no gain while the epilogue bounds the short-K tiles -> opt-in
+  }
   const int sms = num_sms();
   const int cands[4] = {256, 160, 128, 64};
-  float best = 1e30f; int best_bn = 0, best_pair = 0, best_s = 1;
+  float best = 1e30f; int best_bn = 0, best_pair = 0, best_s = 1, best_res = 0;
   for (int pair = 0; pair < 2; ++pair) {
     if (pair && (g_cta2_mode == 1 || M <= 128)) continue;
     // measured on B200 (profiles/): pairing pays only for large, long-K, N % 256 == 0 problems; the 3x3 convs tie
@@ -639,11 +810,25 @@ static void pick_tile(int M, int N, int num_kb, bool geglu, bool conv, int max_s
         if (sp > 1) t += 12000.0f + (float)sp * M * N * 4.0f / (sms * 40.0f);     // slab round trip + reduce launch (sweep_bn)
         const int ctas = (pair ? 2 : 1) * (tiles * sp < units ? tiles * sp : units);
         t *= 1.0f + 0.10f * (1.0f - (float)ctas / (float)sms);     // idle SMs: prefer the finer decomposition
-        if (t < best) { best = t; best_bn = bn; best_pair = pair; best_s = sp; }
+        if (t < best) { best = t; best_bn = bn; best_pair = pair; best_s = sp; best_res = 0; }
+      }
+      // B-resident: one n-tile per CTA, weights loaded once per CTA, only A streams (plain GEMMs, single CTAs)
+      const int tiles_n = N / bn, tiles_m = (M + 127) / 128;
+      if (!pair && !conv && g_bres_mode != 1 && tiles_n <= sms && bres_stages(bn, num_kb) > 0) {
+        const int per_n = sms / tiles_n;
+        if (tiles_m >= 2 * per_n || g_bres_mode == 2) {
+          const int waves = (tiles_m + per_n - 1) / per_n;
+          const float l2a = 3.05f * 128.0f;
+          float t = (float)waves * ((mma > l2a ? mma : l2a) * num_kb + 3000.0f) + 3.05f * bn * num_kb;
+          const int ctas = per_n * tiles_n;
+          t *= 1.0f + 0.10f * (1.0f - (float)ctas / (float)sms);
+          if (g_bres_mode == 2) t = -1.0f / (float)bn;            // test hook: force (widest legal tile)
+          if (t < best) { best = t; best_bn = bn; best_pair = 0; best_s = 1; best_res = 1; }
+        }
       }
     }
   }
-  *bn_out = best_bn; *cta2_out = best_pair; *splits_out = best_s;
+  *bn_out = best_bn; *cta2_out = best_pair; *splits_out = best_s; *bres_out = best_res;
 }
 
 }  // namespace glg
@@ -653,8 +838,12 @@ using namespace glg;
 extern "C" void glg_debug_force_bn(int bn) { glg::g_force_bn = bn; }
 // test hook (host only, no CUDA work): what the tile picker chooses for a problem; out[3] = {BN, paired CTAs, K splits}
 extern "C" void glg_debug_pick_tile(int M, int N, int K, int geglu, int conv, int can_split, long long ws_bytes, int* out) {
-  glg::pick_tile(M, N, (conv ? 9 : 1) * (K / 64), geglu != 0, conv != 0, can_split ? 8 : 1, ws_bytes, &out[0], &out[1], &out[2]);
+  int bres = 0;
+  glg::pick_tile(M, N, (conv ? 9 : 1) * (K / 64), geglu != 0, conv != 0, can_split ? 8 : 1, ws_bytes, &out[0], &out[1], &out[2], &bres);
+  out[1] |= bres << 8;           // bit 8 of the "paired" word: B-resident
 }
+extern "C" void glg_debug_gemm_bres(int mode) { glg::g_bres_mode = mode; }
+extern "C" void glg_debug_gemm_epi(int mode) { glg::g_epi_mode = mode; }
 extern "C" void glg_debug_gemm_cta2(int mode) { glg::g_cta2_mode = mode; }
 extern "C" void glg_debug_splitk(int mode) { glg::g_splitk_mode = mode; }
 
@@ -666,11 +855,11 @@ extern "C" int glg_gemm(const GlgGemmArgs* a, void* stream) {
   if (((uintptr_t)a->A | (uintptr_t)a->W | (uintptr_t)a->out | (uintptr_t)a->residual) & 15) return set_error("glg_gemm: pointers must be 16-byte aligned");
   if (a->rowbias && ((a->ld_rowbias % 4) || a->rows_per_batch <= 0)) return set_error("glg_gemm: bad rowbias args");
   if (a->geglu && (a->N % 256 || !a->bias || a->out_fp32)) return set_error("glg_gemm: geglu needs N % 256 == 0, a bias and bf16 output");
-  int bn = 0, cta2 = 0, splits = 1;
+  int bn = 0, cta2 = 0, splits = 1, bres = 0;
   const bool can_split = a->splitk_ws && g_splitk_mode != 1 && !a->geglu && !a->ln_stats && !a->stats_out && !a->out_fp32 &&
                          !((uintptr_t)a->splitk_ws & 15);
   pick_tile(a->M, a->N, (a->conv_mode ? 9 : 1) * (a->K / 64), a->geglu != 0, a->conv_mode != 0, can_split ? 8 : 1,
-            a->splitk_ws_bytes, &bn, &cta2, &splits);
+            a->splitk_ws_bytes, &bn, &cta2, &splits, &bres);
   if (!bn) return set_error("glg_gemm: N must be a multiple of 64");
   GemmKParams p;
   memset(&p, 0, sizeof(p));
@@ -687,6 +876,7 @@ extern "C" int glg_gemm(const GlgGemmArgs* a, void* stream) {
   if (a->ln_stats) {
     if (!a->ln_colsum || a->ln_slots <= 0 || a->conv_mode) return set_error("glg_gemm: LayerNorm fold needs ln_colsum, ln_slots > 0 and a plain GEMM");
     if (((uintptr_t)a->ln_stats & 7) || ((uintptr_t)a->ln_colsum & 15)) return set_error("glg_gemm: ln_stats / ln_colsum alignment");
+    if (a->ln_slot_stride > 0 && a->ln_slot_stride < a->M) return set_error("glg_gemm: ln_slot_stride < M");
     p.ln_stats = a->ln_stats; p.ln_slots = a->ln_slots; p.ln_colsum = a->ln_colsum; p.ln_eps = a->ln_eps; p.inv_k = 1.0f / (float)a->K;
   }
   if (a->stats_out) {
@@ -704,16 +894,47 @@ extern "C" int glg_gemm(const GlgGemmArgs* a, void* stream) {
 
   p.splits = splits;
   p.ws = splits > 1 ? reinterpret_cast<float*>(a->splitk_ws) : nullptr;
+  p.b_res = bres;
+  // ---- epilogue data path: TMA stores of the bf16 output, TMA loads of the residual (see the kernel comment)
+  static int epi_mode = -1;       // GLG_GEMM_EPI: 0 = per-thread global accesses (the old path), 1 = TMA (default)
+  if (epi_mode < 0) { const char* e = getenv("GLG_GEMM_EPI"); epi_mode = e ? atoi(e) : 1; }
+  const int epi = g_epi_mode >= 0 ? g_epi_mode : epi_mode;
+  p.tma_out = 0; p.tma_res = 0;
+  if (epi && !a->out_fp32 && splits == 1) {
+    if (a->out_rows_per_batch <= 0) p.tma_out = 2;
+    else if (a->out_rows_per_batch % 32 == 0 && a->M % a->out_rows_per_batch == 0) p.tma_out = 3;
+  }
+  if (p.tma_out && a->residual && !a->geglu) p.tma_res = 1;
+  const long long tile_max = 227 * 1024 - 1024 - 1024;
+  const long long stage_bytes = bres ? 16384 : 128 * 128 + (cta2 ? bn / 2 : bn) * 128;
+  const long long fixed = bres ? (long long)p.num_kb * bn * 128 : 0;
+  auto stages_for = [&](int out_on, int res_on) {
+    long long st = (tile_max - fixed - (out_on ? 32768 : 0) - (res_on ? 32768 : 0)) / stage_bytes;
+    const int cap = bres ? 12 : 8;
+    return (int)(st > cap ? cap : st);
+  };
+  // the staging area must not starve the operand ring: long-K tiles keep >= 4 stages (the residual staging goes first)
+  const int min_stages = p.num_kb >= 16 ? 4 : 3;
+  if (p.tma_res && stages_for(1, 1) < min_stages) p.tma_res = 0;
+  if (p.tma_out && stages_for(1, p.tma_res) < min_stages) { p.tma_out = 0; p.tma_res = 0; }
+  p.stages = stages_for(p.tma_out, p.tma_res);
+  if (p.stages < 2) return set_error("glg_gemm: internal: shared memory budget");
+  p.epi_off = (unsigned)(p.stages * stage_bytes + fixed);
+  const size_t smem = (size_t)p.epi_off + (p.tma_out ? 32768 : 0) + (p.tma_res ? 32768 : 0) + 1024 + 1024;
+  if (a->stats_out) p.stats_stride = a->stats_slot_stride > 0 ? a->stats_slot_stride : a->M;
+  if (a->ln_stats) p.ln_stride = a->ln_slot_stride > 0 ? a->ln_slot_stride : a->M;
 
   const uint32_t brows = (uint32_t)(cta2 ? bn / 2 : bn);
   CUtensorMap ta, tb;
   if (a->conv_mode) {
     const int H = a->H, W = a->Wd, B = a->Bn;
     if (H <= 0 || W <= 0 || B <= 0 || (long long)B * H * W != a->M) return set_error("glg_gemm: conv dims do not match M");
-    if (W > 128 || (128 % W)) return set_error("glg_gemm: conv width must divide 128");
+    if ((W <= 128 && (128 % W)) || (W > 128 && (W % 128))) return set_error("glg_gemm: conv width must divide 128 or be a multiple of it");
     const int HW = H * W;
     uint32_t box[4];
-    if (HW >= 128) {
+    if (W > 128) {                 // a 128-pixel tile is a segment of one image row (VAE decoder: 256 / 512 wide)
+      box[0] = 64; box[1] = 128; box[2] = 1; box[3] = 1;
+    } else if (HW >= 128) {
       if (HW % 128) return set_error("glg_gemm: conv H*W must be a multiple of 128 (or divide it)");
       box[0] = 64; box[1] = W; box[2] = 128 / W; box[3] = 1;
     } else {
@@ -738,21 +959,41 @@ extern "C" int glg_gemm(const GlgGemmArgs* a, void* stream) {
     const uint32_t wb[2] = {64, brows};
     if (get_tmap_bf16(&tb, a->W, 2, wd, ws, wb)) return -1;
   }
+  CUtensorMap tout = ta, tres = ta;          // placeholders when unused (never dereferenced by the kernel)
+  if (p.tma_out) {
+    const uint64_t No = a->geglu ? (uint64_t)a->N / 2 : (uint64_t)a->N;
+    const uint32_t box3[3] = {32, 32, 1};
+    if (p.tma_out == 2) {
+      const uint64_t dims[2] = {No, (uint64_t)a->M};
+      const uint64_t str[1] = {(uint64_t)a->ldc * 2};
+      if (get_tmap_bf16_sw(&tout, a->out, 2, dims, str, box3, 64)) return -1;
+    } else {
+      const uint64_t dims[3] = {No, (uint64_t)a->out_rows_per_batch, (uint64_t)(a->M / a->out_rows_per_batch)};
+      const uint64_t str[2] = {(uint64_t)a->ldc * 2, (uint64_t)a->out_batch_stride * 2};
+      if (get_tmap_bf16_sw(&tout, a->out, 3, dims, str, box3, 64)) return -1;
+    }
+  }
+  if (p.tma_res) {
+    const uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->M};
+    const uint64_t str[1] = {(uint64_t)a->ldr * 2};
+    const uint32_t box2[2] = {32, 32};
+    if (get_tmap_bf16_sw(&tres, a->residual, 2, dims, str, box2, 64)) return -1;
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (cta2) {
-    if (a->geglu) return launch_gemm<256, true, true>(ta, tb, p, st);
+    if (a->geglu) return launch_gemm<256, true, true>(ta, tb, tout, tres, p, smem, st);
     switch (bn) {
-      case 256: return launch_gemm<256, false, true>(ta, tb, p, st);
-      case 160: return launch_gemm<160, false, true>(ta, tb, p, st);
-      case 128: return launch_gemm<128, false, true>(ta, tb, p, st);
+      case 256: return launch_gemm<256, false, true>(ta, tb, tout, tres, p, smem, st);
+      case 160: return launch_gemm<160, false, true>(ta, tb, tout, tres, p, smem, st);
+      case 128: return launch_gemm<128, false, true>(ta, tb, tout, tres, p, smem, st);
     }
   } else {
-    if (a->geglu) return launch_gemm<256, true, false>(ta, tb, p, st);
+    if (a->geglu) return launch_gemm<256, true, false>(ta, tb, tout, tres, p, smem, st);
     switch (bn) {
-      case 256: return launch_gemm<256, false, false>(ta, tb, p, st);
-      case 160: return launch_gemm<160, false, false>(ta, tb, p, st);
-      case 128: return launch_gemm<128, false, false>(ta, tb, p, st);
-      case 64:  return launch_gemm<64, false, false>(ta, tb, p, st);
+      case 256: return launch_gemm<256, false, false>(ta, tb, tout, tres, p, smem, st);
+      case 160: return launch_gemm<160, false, false>(ta, tb, tout, tres, p, smem, st);
+      case 128: return launch_gemm<128, false, false>(ta, tb, tout, tres, p, smem, st);
+      case 64:  return launch_gemm<64, false, false>(ta, tb, tout, tres, p, smem, st);
     }
   }
   return set_error("glg_gemm: internal: bad tile");

@@ -32,34 +32,70 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
-// ---- GroupNorm pass 1: per-(batch, group) mean / rstd, DETERMINISTIC ---------------------------------
-// grid (chunks, B); blockDim = (C/8) * rpi, thread -> (fixed channel vector cv, row lane rl).
-// Each CTA writes its per-group partial (sum, sumsq) to scratch; the last CTA of a batch (atomic ticket)
-// reduces the partials in chunk order - no floating-point atomics on the result, so a forward is
-// bit-reproducible run to run.
-// scratch layout (floats): ticket[64] (uint, zero before the first use, reset by the last CTA) | final[B][G][2] (sum, sumsq)
-//                          | partial[B][chunks][G][2]
-__global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float* __restrict__ scratch,
-                                int B, int HW, int C, int groups, int rows_per_chunk) {
+// ---- GroupNorm, ONE kernel: statistics -> per-sample barrier -> normalise + affine (+SiLU) ---------------------
+// grid (chunks, B), every CTA co-resident (the launcher sizes the grid by the occupancy of this kernel);
+// blockDim = (C/8) * rpi, thread -> (fixed channel vector cv of 8 channels, row lane rl); a CTA owns rows
+// [chunk * rows_per_chunk, ...) of one sample.
+//   1. pivot: p_g = mean of row 0 of the sample over the group's channels (every CTA of a sample computes the same
+//      value in the same order).  All moments are accumulated on SHIFTED data d = x - p_g, so the variance
+//      S2/n - (S1/n)^2 never subtracts two large numbers (the raw E[x^2] - E[x]^2 form loses everything when
+//      |mean| >> std; util.py:223-225 runs F.group_norm in fp32, which is a two-pass / Welford computation).
+//   2. per-CTA partial (S1, S2) per group -> scratch; sample-wide barrier (arrive counter + spin; the counters reset
+//      themselves when the last CTA leaves); every CTA then sums the partials of its sample in chunk order: no
+//      floating-point atomics anywhere, a forward is bit-reproducible run to run.
+//   3. apply: the activation is read a second time (an L2 hit: producer -> GroupNorm -> consumer tensors of this
+//      model fit the 126 MB L2) and written once.
+// scratch layout (32-bit words): arrive[64] | depart[64] (uint, zero before the first use, self-resetting)
+//                                | partial[B][chunks][G][2] fp32
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+__global__ void gn_fused_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ scratch,
+                                int B, int HW, int C, int groups, float eps, int silu, int rows_per_chunk) {
   pdl_trigger();
   pdl_wait();
-  extern __shared__ float gn_sm[];          // [2][max(C, 512)]
-  __shared__ bool is_last;
+  extern __shared__ float gn_sm[];          // [2][max(C, 512)] | pivot[groups] | mean[groups] | rstd[groups]
+  const int cmax = C > 512 ? C : 512;
   float* s_sum = gn_sm;
-  float* s_sq = gn_sm + (C > 512 ? C : 512);
+  float* s_sq = gn_sm + cmax;
+  float* s_piv = gn_sm + 2 * cmax;
+  float* s_mean = s_piv + groups;
+  float* s_rstd = s_mean + groups;
   const int vec = C >> 3;
   const int rpi = blockDim.x / vec;
   const int cv = threadIdx.x % vec, rl = threadIdx.x / vec;
   const int b = blockIdx.y, chunks = gridDim.x;
-  unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch) + b;
-  float* fin = scratch + 64 + (long long)b * groups * 2;
-  float* part = scratch + 64 + (long long)B * groups * 2 + ((long long)b * chunks + blockIdx.x) * groups * 2;
+  const int cpg = C / groups;
+  unsigned int* arrive = reinterpret_cast<unsigned int*>(scratch) + b;
+  unsigned int* depart = reinterpret_cast<unsigned int*>(scratch) + 64 + b;
+  float* part_b = scratch + 128 + (long long)b * chunks * groups * 2;
+  const bf16* xb = x + (long long)b * HW * ldx + cv * 8;
+
+  // ---- 1. pivots from row 0
+  if (rl == 0) {
+    float v[8];
+    load8(xb, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_sum[cv * 8 + j] = v[j];
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float s = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) s += s_sum[c];
+    s_piv[g] = s / (float)cpg;
+  }
+  __syncthreads();
+  float pv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) pv[j] = s_piv[(cv * 8 + j) / cpg];
+  __syncthreads();                           // s_sum is reused below
+
+  // ---- 2. shifted moments of this CTA's rows
   const int r0 = blockIdx.x * rows_per_chunk;
   const int r1 = min(HW, r0 + rows_per_chunk);
   float a[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a[j] = 0.f; q[j] = 0.f; }
-  const bf16* xb = x + (long long)b * HW * ldx + cv * 8;
   int r = r0 + rl;
   for (; r + 3 * rpi < r1; r += 4 * rpi) {      // 4 independent 16-byte loads in flight per thread
     uint4 u[4];
@@ -70,14 +106,14 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float
       float v[8];
       unpack8(u[i], v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { a[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+      for (int j = 0; j < 8; ++j) { const float d = v[j] - pv[j]; a[j] += d; q[j] = fmaf(d, d, q[j]); }
     }
   }
   for (; r < r1; r += rpi) {
     float v[8];
     load8(xb + (long long)r * ldx, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { a[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+    for (int j = 0; j < 8; ++j) { const float d = v[j] - pv[j]; a[j] += d; q[j] = fmaf(d, d, q[j]); }
   }
   // fixed-order reduction over the rpi row lanes: lane rl == k adds in turn
   for (int k = 0; k < rpi; ++k) {
@@ -90,28 +126,38 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float
     }
     __syncthreads();
   }
-  const int cpg = C / groups;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     float s = 0.f, ss = 0.f;
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) { s += s_sum[c]; ss += s_sq[c]; }
-    part[g * 2 + 0] = s;
-    part[g * 2 + 1] = ss;
+    *reinterpret_cast<float2*>(part_b + ((long long)blockIdx.x * groups + g) * 2) = make_float2(s, ss);
   }
-  __threadfence();
+  // ---- sample-wide barrier: every CTA of sample b has published its partials
   __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == (unsigned)chunks - 1u);
-  __syncthreads();
-  if (is_last) {
+  if (threadIdx.x == 0) {
     __threadfence();
-    // last CTA of this sample: reduce the per-chunk partials.  Fixed order (deterministic) but spread over the whole
-    // block: thread (g, part) sums chunks part, part + P, ... ; then the P partial sums are added in order.
-    const float* pb = scratch + 64 + (long long)B * groups * 2 + (long long)b * chunks * groups * 2;
-    const int P = blockDim.x / groups;                 // groups = 32: P = 7..10 row lanes
+    atomicAdd(arrive, 1u);
+    unsigned int seen;
+    unsigned long long t0 = 0;
+    while (true) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrive) : "memory");
+      if (seen >= (unsigned)chunks) break;
+      __nanosleep(64);
+      if (t0 == 0) t0 = globaltimer_ns();
+      else if (globaltimer_ns() - t0 > 4000000000ull) {   // co-residency violated: trap instead of hanging the box
+        printf("glg: groupnorm barrier timeout (sample %d chunk %d: %u of %d arrived)\n", b, blockIdx.x, seen, chunks);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  {
+    // fixed order, spread over the block: thread (g, part) sums chunks part, part + P, ...; then the P sums in order
+    const int P = blockDim.x / groups;
     const int g = threadIdx.x % groups, part = threadIdx.x / groups;
-    float s = 0.f, ss = 0.f;
     if (part < P) {
+      float s = 0.f, ss = 0.f;
       for (int k = part; k < chunks; k += P) {
-        const float2 t = __ldcg(reinterpret_cast<const float2*>(pb + ((long long)k * groups + g) * 2));
+        const float2 t = __ldcg(reinterpret_cast<const float2*>(part_b + ((long long)k * groups + g) * 2));
         s += t.x; ss += t.y;
       }
       s_sum[part * groups + g] = s;                    // P * groups <= blockDim <= 512 floats per half
@@ -121,48 +167,35 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, long long ldx, float
     if (threadIdx.x < groups) {
       float ts = 0.f, tss = 0.f;
       for (int i = 0; i < P; ++i) { ts += s_sum[i * groups + threadIdx.x]; tss += s_sq[i * groups + threadIdx.x]; }
-      fin[threadIdx.x * 2] = ts;
-      fin[threadIdx.x * 2 + 1] = tss;
+      const float inv_n = 1.f / ((float)HW * (float)cpg);
+      const float m1 = ts * inv_n;                                       // mean of the shifted data
+      const float var = fmaxf(tss * inv_n - m1 * m1, 0.f);
+      s_mean[threadIdx.x] = s_piv[threadIdx.x] + m1;
+      s_rstd[threadIdx.x] = rsqrtf(var + eps);
     }
-    if (threadIdx.x == 0) *ticket = 0u;       // ready for the next GroupNorm on this scratch (stream-ordered)
+    if (threadIdx.x == 0) {
+      // everyone who reaches this point has left the spin loop: the last one out re-arms the counters
+      if (atomicAdd(depart, 1u) == (unsigned)chunks - 1u) { *depart = 0u; *arrive = 0u; __threadfence(); }
+    }
+    __syncthreads();
   }
-}
 
-// ---- GroupNorm pass 2: normalise + affine (+SiLU) -----------------------------------------------
-// Same thread -> (channel vector, row lane) mapping as pass 1: the 8 scale/shift pairs of a thread live in
-// registers, the row loop is a pure 16-byte load / 8 FMA (+SiLU) / 16-byte store stream.
-__global__ void gn_apply_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
-                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                const float* __restrict__ stats, int HW, int C, int groups, float eps, int silu,
-                                int rows_per_chunk) {
-  pdl_trigger();
-  pdl_wait();
-  const int vec = C >> 3;
-  const int rpi = blockDim.x / vec;
-  const int cv = threadIdx.x % vec, rl = threadIdx.x / vec;
-  const int b = blockIdx.y;
-  const int cpg = C / groups;
-  const float inv_n = 1.f / ((float)HW * (float)cpg);
+  // ---- 3. normalise + affine (+SiLU): 16-byte load / 8 FMA (+SiLU) / 16-byte store stream
   float sa[8], sb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = cv * 8 + j;
     const int g = c / cpg;
-    const float mean = stats[64 + ((long long)b * groups + g) * 2] * inv_n;
-    const float var = fmaxf(stats[64 + ((long long)b * groups + g) * 2 + 1] * inv_n - mean * mean, 0.f);
-    const float ga = gamma[c] * rsqrtf(var + eps);
+    const float ga = __ldg(gamma + c) * s_rstd[g];
     sa[j] = ga;
-    sb[j] = beta[c] - mean * ga;
+    sb[j] = __ldg(beta + c) - s_mean[g] * ga;
   }
-  const int r0 = blockIdx.x * rows_per_chunk;
-  const int r1 = min(HW, r0 + rows_per_chunk);
-  const bf16* xb = x + (long long)b * HW * ldx + cv * 8;
   bf16* yb = y + (long long)b * HW * ldy + cv * 8;
-  int r = r0 + rl;
+  r = r0 + rl;
   for (; r + 3 * rpi < r1; r += 4 * rpi) {
     uint4 u[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) u[i] = __ldg(reinterpret_cast<const uint4*>(xb + (long long)(r + i * rpi) * ldx));
+    for (int i = 0; i < 4; ++i) u[i] = __ldcg(reinterpret_cast<const uint4*>(xb + (long long)(r + i * rpi) * ldx));
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float v[8];
@@ -170,18 +203,19 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, long long ldx, bf16*
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float t = fmaf(v[j], sa[j], sb[j]);
-        v[j] = silu ? silu_f(t) : t;
+        v[j] = silu ? silu_fast(t) : t;
       }
       store8(yb + (long long)(r + i * rpi) * ldy, v);
     }
   }
   for (; r < r1; r += rpi) {
     float v[8];
-    load8(xb + (long long)r * ldx, v);
+    const uint4 u = __ldcg(reinterpret_cast<const uint4*>(xb + (long long)r * ldx));
+    unpack8(u, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float t = fmaf(v[j], sa[j], sb[j]);
-      v[j] = silu ? silu_f(t) : t;
+      v[j] = silu ? silu_fast(t) : t;
     }
     store8(yb + (long long)r * ldy, v);
   }
@@ -195,17 +229,28 @@ __global__ void gn_small_kernel(const bf16* __restrict__ x, long long ldx, bf16*
   pdl_trigger();
   pdl_wait();
   __shared__ float red[2][32];
+  __shared__ float s_pivot;
   const int g = blockIdx.x, b = blockIdx.y;
   const int cpg = C / groups, half = cpg >> 1;        // cpg is even: process bf16 pairs
   const int total = HW * half;
   const bf16* xb = x + (long long)b * HW * ldx + g * cpg;
   bf16* yb = y + (long long)b * HW * ldy + g * cpg;
+  // pivot = mean of the group's channels in row 0; moments are taken on x - pivot (see gn_fused_kernel)
+  if (threadIdx.x < 32) {
+    float ps = 0.f;
+    for (int c = threadIdx.x; c < cpg; c += 32) ps += __bfloat162float(xb[c]);
+    ps = warp_sum(ps);
+    if (threadIdx.x == 0) s_pivot = ps / (float)cpg;
+  }
+  __syncthreads();
+  const float pivot = s_pivot;
   float s = 0.f, ss = 0.f;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int r = i / half, c2 = i - r * half;
     const float2 f = unpack_bf16x2(__ldg(reinterpret_cast<const uint32_t*>(xb + (long long)r * ldx + c2 * 2)));
-    s += f.x + f.y;
-    ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss));
+    const float d0 = f.x - pivot, d1 = f.y - pivot;
+    s += d0 + d1;
+    ss = fmaf(d0, d0, fmaf(d1, d1, ss));
   }
   s = warp_sum(s); ss = warp_sum(ss);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -214,8 +259,9 @@ __global__ void gn_small_kernel(const bf16* __restrict__ x, long long ldx, bf16*
   float ts = 0.f, tss = 0.f;
   for (int w = 0; w < nw; ++w) { ts += red[0][w]; tss += red[1][w]; }      // fixed order: deterministic
   const float inv_n = 1.f / (float)(HW * cpg);
-  const float mean = ts * inv_n;
-  const float rstd = rsqrtf(fmaxf(tss * inv_n - mean * mean, 0.f) + eps);
+  const float m1 = ts * inv_n;
+  const float mean = pivot + m1;
+  const float rstd = rsqrtf(fmaxf(tss * inv_n - m1 * m1, 0.f) + eps);
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int r = i / half, c2 = i - r * half;
     const int c = g * cpg + c2 * 2;
@@ -223,7 +269,7 @@ __global__ void gn_small_kernel(const bf16* __restrict__ x, long long ldx, bf16*
     const float g0 = gamma[c] * rstd, g1 = gamma[c + 1] * rstd;
     float t0 = fmaf(f.x, g0, beta[c] - mean * g0);
     float t1 = fmaf(f.y, g1, beta[c + 1] - mean * g1);
-    if (silu) { t0 = silu_f(t0); t1 = silu_f(t1); }
+    if (silu) { t0 = silu_fast(t0); t1 = silu_fast(t1); }
     *reinterpret_cast<uint32_t*>(yb + (long long)r * ldy + c2 * 2) = pack_bf16x2(t0, t1);
   }
 }
@@ -302,21 +348,29 @@ extern "C" int glg_groupnorm(const void* x, int64_t ldx, void* y, int64_t ldy, c
   int rpi = 256 / vec; if (rpi < 1) rpi = 1;
   const int threads = vec * rpi;          // <= 512 for C <= 4096
   if (threads > 1024) return set_error("glg_groupnorm: C too large for one block");
-  int chunks = (4 * 148 + B - 1) / B;
-  int max_chunks = (HW + rpi * 4 - 1) / (rpi * 4);
+  if (B > 64) return set_error("glg_groupnorm: at most 64 samples per call");
+  const size_t smem = (2 * (size_t)(C > 512 ? C : 512) + 3 * (size_t)groups) * sizeof(float);
+  // every CTA of the grid must be resident at once (sample-wide barrier inside the kernel)
+  static int occ_cache[5] = {0, 0, 0, 0, 0};            // by block size class: occupancy of gn_fused_kernel
+  const int cls = threads <= 160 ? 0 : threads <= 256 ? 1 : threads <= 320 ? 2 : threads <= 512 ? 3 : 4;
+  if (!occ_cache[cls]) {
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_fused_kernel, threads, 2 * 4096 * sizeof(float) + 3 * 64 * sizeof(float));
+    if (e != cudaSuccess || occ < 1) return set_error(std::string("glg_groupnorm: occupancy query failed: ") + cudaGetErrorString(e));
+    occ_cache[cls] = occ > 8 ? 8 : occ;
+  }
+  const int capacity = num_sms() * occ_cache[cls];
+  int chunks = capacity / B;
+  const int max_chunks = (HW + rpi * 4 - 1) / (rpi * 4);
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
   const int rows_per_chunk = (HW + chunks - 1) / chunks;
   chunks = (HW + rows_per_chunk - 1) / rows_per_chunk;
+  if (128 + (long long)B * chunks * groups * 2 > (long long)GLG_GN_SCRATCH_FLOATS(B, groups)) return set_error("glg_groupnorm: internal scratch sizing");
   dim3 grid(chunks, B);
-  if (B > 64) return set_error("glg_groupnorm: at most 64 samples per call");
-  if (64 + (long long)B * groups * 2 * (1 + chunks) > (long long)GLG_GN_SCRATCH_FLOATS(B, groups)) return set_error("glg_groupnorm: internal scratch sizing");
-  launch_k(gn_stats_kernel, dim3(grid), dim3(threads), 2 * (C > 512 ? C : 512) * sizeof(float), st, 1, (const bf16*)x, ldx, stats, B, HW, C, groups, rows_per_chunk);
+  launch_k(gn_fused_kernel, dim3(grid), dim3(threads), smem, st, 1, (const bf16*)x, ldx, (bf16*)y, ldy, gamma, beta, stats, B, HW, C, groups, eps, silu, rows_per_chunk);
   count_launch();
-  if (check_launch("gn_stats launch")) return -1;
-  launch_k(gn_apply_kernel, dim3(grid), dim3(threads), 0, st, 1, (const bf16*)x, ldx, (bf16*)y, ldy, gamma, beta, stats, HW, C, groups, eps, silu, rows_per_chunk);
-  count_launch();
-  return check_launch("gn_apply launch");
+  return check_launch("gn_fused launch");
 }
 
 extern "C" int glg_layernorm(const void* x, int64_t x_batch, void* y, int64_t y_batch, const float* gamma, const float* beta,

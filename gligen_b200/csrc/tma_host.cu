@@ -29,7 +29,7 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 struct TmapKey {
-  const void* ptr; uint64_t d[4]; uint64_t s[3]; uint32_t box[4]; int rank;
+  const void* ptr; uint64_t d[4]; uint64_t s[3]; uint32_t box[4]; int rank; int swizzle;
   bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
 };
 struct TmapKeyHash {
@@ -46,9 +46,15 @@ static std::mutex g_tmap_mu;
 // bf16 tensor map, 128B swizzle, zero OOB fill.  dims/strides innermost first; strides in bytes (rank-1 of them).
 int get_tmap_bf16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
                   const uint32_t* box) {
+  return get_tmap_bf16_sw(out, ptr, rank, dims, strides, box, 128);
+}
+
+// same with the swizzle width chosen by the caller (64: the epilogue's [32 x 32] staging chunks, inner box = 64 bytes)
+int get_tmap_bf16_sw(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
+                     const uint32_t* box, int swizzle_bytes) {
   TmapKey key;
   memset(&key, 0, sizeof(key));
-  key.ptr = ptr; key.rank = rank;
+  key.ptr = ptr; key.rank = rank; key.swizzle = swizzle_bytes;
   for (int i = 0; i < rank; ++i) { key.d[i] = dims[i]; key.box[i] = box[i]; }
   for (int i = 0; i < rank - 1; ++i) key.s[i] = strides[i];
   std::lock_guard<std::mutex> lk(g_tmap_mu);
@@ -61,7 +67,7 @@ int get_tmap_bf16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* d
   for (int i = 0; i < rank - 1; ++i) gs[i] = strides[i];
   CUtensorMap m;
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];

@@ -56,6 +56,36 @@ def broadcast_module_weights(module: torch.nn.Module, src: int = 0, bucket_numel
     return sent
 
 
+def broadcast_tensors(tensors, src: int = 0, bucket_bytes: int = 512 << 20) -> int:
+    """Broadcast a list of tensors in place, in list order, as flat per-dtype buckets of <= bucket_bytes (few large
+    NCCL calls instead of one per tensor).  Every rank must pass tensors of identical shapes / dtypes.  Returns bytes sent."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 0
+    sent = 0
+    by_dtype: Dict[torch.dtype, list] = {}
+    for t in tensors:
+        by_dtype.setdefault(t.dtype, []).append(t)
+    for dtype, ts in by_dtype.items():
+        i = 0
+        while i < len(ts):
+            bucket, nbytes = [], 0
+            while i < len(ts) and (not bucket or nbytes + ts[i].numel() * ts[i].element_size() <= bucket_bytes):
+                bucket.append(ts[i])
+                nbytes += ts[i].numel() * ts[i].element_size()
+                i += 1
+            if len(bucket) == 1 and bucket[0].is_contiguous():
+                dist.broadcast(bucket[0], src=src)
+            else:
+                flat = torch.cat([t.reshape(-1) for t in bucket])
+                dist.broadcast(flat, src=src)
+                off = 0
+                for t in bucket:
+                    t.copy_(flat[off: off + t.numel()].view_as(t))
+                    off += t.numel()
+            sent += nbytes
+    return sent
+
+
 def gather_latents(latent: torch.Tensor) -> torch.Tensor:
     """All-gather the per-rank [B/n, 4, H, W] latents into the global batch order (equal shards)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

@@ -19,6 +19,7 @@ from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
 
+from .ops import gn_scratch_floats
 from .spec import UNetConfig, block_schedule
 
 ACT_NONE, ACT_SILU = 0, 1
@@ -185,6 +186,20 @@ class Engine:
             P.static_sig = None
         self.set_scale(self.scale)
 
+    def broadcast_packed(self, src: int = 0) -> int:
+        """Frozen weights, once, over NCCL / NVLink (north star): send the PACKED arena of `src` - bf16 GEMM /
+        conv operands in their fused layouts (2.14 GB for SD-1.4 + GLIGEN) plus the small fp32 vectors - instead of the
+        fp32 masters (4.3 GB).  Every rank must have called load_state_dict (any values) so the slots exist.
+        Returns the bytes sent."""
+        from .dist import broadcast_tensors
+        assert self.loaded, "load_state_dict first (allocates the packed slots)"
+        names = sorted(k for k in self.W if k != "gates")
+        sent = broadcast_tensors([self.W[k] for k in names], src=src)
+        self.weights_version += 1
+        self.invalidate_static()
+        self.set_scale(self.scales)
+        return sent
+
     def _pack_position_net(self, sd) -> None:
         cfg, W, pn = self.cfg, self.W, "position_net"
 
@@ -279,7 +294,7 @@ class Engine:
         sz = self._sizes(Bt, N, nctx)
         B_ = {k: self._buf(v, torch.float32 if k == "xstat" else None) for k, v in sz.items()}
         B_["blk2"] = self._buf(sz["blk"])
-        stats = torch.zeros(2 * 32 * (Bt + 4 * 148 + 2 * Bt) + Bt + 64, device=self.dev, dtype=torch.float32)   # GLG_GN_SCRATCH_FLOATS, tickets zeroed once
+        stats = torch.zeros(gn_scratch_floats(Bt), device=self.dev, dtype=torch.float32)   # GLG_GN_SCRATCH_FLOATS, barrier counters zeroed once
         Himg = cfg.image_size
         f32 = torch.float32
 
@@ -396,7 +411,7 @@ class Engine:
             ao = view("ao", Bt, T, C)
             ffh = view("ffh", Bt, T, 4 * C)
             qkv = view("qkv", Bt, T, 3 * C)
-            xst = view("xstat", Bt * T, NS, 2)             # (sum, sumsq) partials of the CURRENT xs rows
+            xst = view("xstat", NS, Bt * T, 2)             # slot-major (sum, sumsq) partials of the CURRENT xs rows
             EPS = 1e-5
             P.add(f"{p}.gn", lambda: ops.groupnorm(x_in, t0, W[f"{p}.gn.g"], W[f"{p}.gn.b"], stats, 32, 1e-6, False))
             P.add(f"{p}.proj_in", lambda: ops.gemm(t0, W[f"{p}.proj_in.w"], xs, bias=W[f"{p}.proj_in.b"], stats_out=xst))
@@ -410,14 +425,14 @@ class Engine:
             #    visual rows every step, the grounding rows (objs' = linear(objs) is timestep-invariant) once.
             fu = f"{tb}.fuser"
             objp = self._buf(S * Bt * N * C).view(S, Bt * N, C)
-            ostat = self._buf(S * Bt * N * NS * 2, f32).view(S, Bt * N, NS, 2)
+            ostat = self._buf(S * Bt * N * NS * 2, f32).view(NS, S * Bt * N, 2)     # slot-major over all streams' rows
             qkv2 = self._buf(Bt * (T + G) * 3 * C).view(Bt, T + G, 3 * C)
             P.add(f"{fu}.linear", lambda: ops.gemm(objs.view(S * Bt * N, D), W[f"{fu}.linear.w"], objp.view(S * Bt * N, C),
-                                                  bias=W[f"{fu}.linear.b"], stats_out=ostat.view(S * Bt * N, NS, 2)), fuser=True, static=True)
+                                                  bias=W[f"{fu}.linear.b"], stats_out=ostat), fuser=True, static=True)
             for si in range(S):
                 P.add(f"{fu}.attn.qkv.objs{si}", lambda si=si: ops.gemm(
                     objp[si], W[f"{fu}.attn.qkv.w"], qkv2[:, T + si * N: T + (si + 1) * N], bias=W[f"{fu}.attn.qkv.b"],
-                    ln=(ostat[si], W[f"{fu}.attn.qkv.s"], EPS)), fuser=True, static=True)
+                    ln=(ostat[:, si * Bt * N: (si + 1) * Bt * N], W[f"{fu}.attn.qkv.s"], EPS)), fuser=True, static=True)
             P.add(f"{fu}.attn.qkv", lambda: ops.gemm(xs, W[f"{fu}.attn.qkv.w"], qkv2[:, :T], bias=W[f"{fu}.attn.qkv.b"],
                                                     ln=(xst, W[f"{fu}.attn.qkv.s"], EPS)), fuser=True)
             P.add(f"{fu}.attn.core", lambda: ops.attention(qkv2[:, :T, :C], qkv2[:, :, C:2 * C], qkv2[:, :, 2 * C:], ao, heads, d), fuser=True)

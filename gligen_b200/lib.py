@@ -25,6 +25,7 @@ class GlgGemmArgs(C.Structure):
         ("ln_stats", c_void_p), ("ln_colsum", c_void_p), ("ln_slots", c_int), ("ln_eps", c_float),
         ("stats_out", c_void_p), ("stats_slots", c_int), ("out_rows_per_batch", c_int), ("out_batch_stride", c_int64),
         ("splitk_ws", c_void_p), ("splitk_ws_bytes", c_int64),
+        ("ln_slot_stride", c_int64), ("stats_slot_stride", c_int64),
     ]
 
 
@@ -62,7 +63,7 @@ SIGNATURES = {
                                    c_float, c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 # not part of the public header: test hook
-_DEBUG_SIGNATURES = {"glg_debug_force_bn": (None, [c_int]), "glg_debug_pick_tile": (None, [c_int, c_int, c_int, c_int, c_int, c_int, c_int64, C.POINTER(c_int)]), "glg_debug_attn_mode": (None, [c_int]), "glg_debug_attn_poly": (None, [c_int]), "glg_debug_attn_probe": (None, [c_void_p]), "glg_debug_attn_tc_variant": (None, [c_int]), "glg_debug_gemm_cta2": (None, [c_int]), "glg_debug_splitk": (None, [c_int])}
+_DEBUG_SIGNATURES = {"glg_debug_force_bn": (None, [c_int]), "glg_debug_pick_tile": (None, [c_int, c_int, c_int, c_int, c_int, c_int, c_int64, C.POINTER(c_int)]), "glg_debug_attn_mode": (None, [c_int]), "glg_debug_attn_poly": (None, [c_int]), "glg_debug_attn_probe": (None, [c_void_p]), "glg_debug_attn_tc_variant": (None, [c_int]), "glg_debug_gemm_cta2": (None, [c_int]), "glg_debug_splitk": (None, [c_int]), "glg_debug_gemm_bres": (None, [c_int]), "glg_debug_gemm_epi": (None, [c_int])}
 
 _lib: Optional[C.CDLL] = None
 
@@ -86,7 +87,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.glg_abi_version() != 2:
+    if lib.glg_abi_version() != 3:
         raise GligenLibraryError(f"ABI mismatch: library reports {lib.glg_abi_version()}")
     _lib = lib
     return lib

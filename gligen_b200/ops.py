@@ -30,6 +30,11 @@ def _rows_view(t: torch.Tensor):
     return t.data_ptr(), rows, cols, ld
 
 
+def gn_scratch_floats(B: int, groups: int = 32) -> int:
+    """GLG_GN_SCRATCH_FLOATS of include/gligen_b200.h (the first 128 words must be zero before the first call)."""
+    return 128 + 2 * groups * (8 * 148 + B)
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -67,8 +72,9 @@ class CudaOps:
     def gemm(self, a, w, out, bias=None, rowbias=None, rows_per_batch=1, act=0, gate=None, residual=None,
              geglu=False, conv=None, ln=None, stats_out=None):
         """out = epilogue(a @ w.T).  `conv=(B,H,W)` selects the implicit 3x3 convolution (w is [9*N, K]).
-        ln=(stats [M,S,2] fp32, colsum [N] fp32, eps): LayerNorm of the A rows folded into the epilogue.
-        stats_out [M,S,2] fp32: per-row partial (sum, sumsq) of the stored output.
+        ln=(stats [S,M,2] fp32 slot-major, colsum [N] fp32, eps): LayerNorm of the A rows folded into the epilogue.
+        stats_out [S,M,2] fp32: per-row partial (sum, sumsq) of the stored output, one slot per 32 columns.
+        Both may be row ranges of a larger [S, rows, 2] tensor (views `t[:, lo:hi]`): the slot stride is passed on.
         `out` may be a [B, rows, N] view whose batch stride is not rows*ld (batch-strided rows)."""
         ap, M, K, lda = _rows_view(a)
         g = L.GlgGemmArgs()
@@ -107,16 +113,18 @@ class CudaOps:
             g.conv_mode, g.Bn, g.H, g.Wd = 0, 0, 0, 0
         if ln is not None:
             st, colsum, eps = ln
-            assert st.dtype == torch.float32 and st.is_contiguous() and st.shape[0] == M and st.shape[2] == 2
+            assert st.dtype == torch.float32 and st.dim() == 3 and st.shape[1] == M and st.shape[2] == 2 and st.stride(2) == 1 and st.stride(1) == 2
             assert colsum.dtype == torch.float32 and colsum.numel() == N
-            g.ln_stats, g.ln_colsum, g.ln_slots, g.ln_eps = st.data_ptr(), colsum.data_ptr(), st.shape[1], eps
+            g.ln_stats, g.ln_colsum, g.ln_slots, g.ln_eps = st.data_ptr(), colsum.data_ptr(), st.shape[0], eps
+            g.ln_slot_stride = st.stride(0) // 2
         else:
-            g.ln_stats, g.ln_colsum, g.ln_slots, g.ln_eps = None, None, 0, 0.0
+            g.ln_stats, g.ln_colsum, g.ln_slots, g.ln_eps, g.ln_slot_stride = None, None, 0, 0.0, 0
         if stats_out is not None:
-            assert stats_out.dtype == torch.float32 and stats_out.is_contiguous() and stats_out.shape[0] == M and stats_out.shape[2] == 2
-            g.stats_out, g.stats_slots = stats_out.data_ptr(), stats_out.shape[1]
+            so = stats_out
+            assert so.dtype == torch.float32 and so.dim() == 3 and so.shape[1] == M and so.shape[2] == 2 and so.stride(2) == 1 and so.stride(1) == 2
+            g.stats_out, g.stats_slots, g.stats_slot_stride = so.data_ptr(), so.shape[0], so.stride(0) // 2
         else:
-            g.stats_out, g.stats_slots = None, 0
+            g.stats_out, g.stats_slots, g.stats_slot_stride = None, 0, 0
         g.splitk_ws, g.splitk_ws_bytes = self.splitk_ws.data_ptr(), self.splitk_ws.numel() * 4
         L.check(self.lib.glg_gemm(C.byref(g), self._stream()), "glg_gemm")
         taps = 9 if conv is not None else 1

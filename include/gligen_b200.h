@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GLG_ABI_VERSION 2
+#define GLG_ABI_VERSION 3
 
 #define GLG_ACT_NONE 0
 #define GLG_ACT_SILU 1
@@ -53,10 +53,11 @@ void glg_reset_launch_count(void);
  *   channel, folded into W by the caller), colsum[n] = sum_k W'[n,k] and bias' = bias + W beta,
  *       LN(x) W^T + bias = rstd_r * (x W'^T - mu_r * colsum) + bias'
  *   so the GEMM runs on the RAW activations and the normalisation is two per-row scalars in the epilogue:
- *   ln_stats[M][ln_slots][2] holds partial (sum, sum of squares) of every A row over its K columns (summed in
+ *   ln_stats[ln_slots][rows][2] holds partial (sum, sum of squares) of every A row over its K columns (summed in
  *   slot order); they are produced for free by the GEMM that wrote A when its stats_out is set
- *   (stats_out[M][N/32][2]: one partial per (row, 32-column chunk) of the bf16-rounded stored values - a layout
- *   independent of the tile shape, so results are bit-reproducible).  No LayerNorm kernel, no normalised copy in HBM.
+ *   (stats_out[N/32][rows][2]: one partial per (row, 32-column chunk) of the bf16-rounded stored values - a layout
+ *   independent of the tile shape, so results are bit-reproducible; slot-major so that the 32 rows a warp owns are
+ *   contiguous).  No LayerNorm kernel, no normalised copy in HBM.
  * out_rows_per_batch > 0: output row r is written at (r / orpb) * out_batch_stride + (r % orpb) * ldc.
  * splitk_ws: when the tile grid would leave most SMs idle (M = 64 * batch at the 8x8 level) up to 8 CTAs share an
  *   output tile, each reducing a contiguous K range into an fp32 slab; a second kernel sums the slabs in a fixed
@@ -81,16 +82,18 @@ typedef struct GlgGemmArgs {
   int32_t geglu;
   int32_t conv_mode;      /* 0 = plain GEMM, 1 = 3x3 stride-1 pad-1 convolution */
   int32_t H, Wd, Bn;      /* conv_mode: spatial dims and batch; M == Bn*H*Wd */
-  const float* ln_stats;  /* LayerNorm fold: [M, ln_slots, 2] fp32 or NULL */
+  const float* ln_stats;  /* LayerNorm fold: SLOT-major [ln_slots][ln_slot_stride rows][2] fp32 or NULL */
   const float* ln_colsum; /* [N] fp32 */
   int32_t ln_slots;
   float ln_eps;
-  float* stats_out;       /* [M, stats_slots, 2] fp32 or NULL */
+  float* stats_out;       /* SLOT-major [stats_slots][stats_slot_stride rows][2] fp32 or NULL */
   int32_t stats_slots;
   int32_t out_rows_per_batch;
   int64_t out_batch_stride;
   void* splitk_ws;        /* optional fp32 scratch for split-K (small-M, long-K problems); NULL disables it */
   int64_t splitk_ws_bytes;
+  int64_t ln_slot_stride;    /* rows between consecutive slots of ln_stats (0 = M): lets a consumer read a row range of a */
+  int64_t stats_slot_stride; /* larger producer's statistics (the grounding-token streams) */
 } GlgGemmArgs;
 int glg_gemm(const GlgGemmArgs* args, void* stream);
 
@@ -119,10 +122,12 @@ int glg_attention(const GlgAttnArgs* args, void* stream);
  * GroupNorm over channels-last input (32 groups in the reference): fp32 statistics, affine, optional
  * SiLU, bf16 out.  Replaces GroupNorm32+SiLU (util.py:208-226, openaimodel.py:155-156,179-180,392-393;
  * eps 1e-5) and Normalize (attention.py:76-77; eps 1e-6, no SiLU).  `stats` is a caller-provided fp32
- * scratch of GLG_GN_SCRATCH_FLOATS(B, groups) floats whose first 64 words must be ZERO before the first call (they
- * hold self-resetting tickets; per-CTA partials are reduced in a fixed order: results are bit-reproducible). B <= 64.
+ * scratch of GLG_GN_SCRATCH_FLOATS(B, groups) floats whose first 128 words must be ZERO before the first call (they
+ * hold the self-resetting counters of a sample-wide barrier inside the single kernel; per-CTA partial moments -
+ * accumulated on data shifted by a per-group pivot, so large-mean activations do not cancel - are reduced in a fixed
+ * order: results are bit-reproducible).  B <= 64.  One launch; the grid is sized so that all CTAs are co-resident.
  */
-#define GLG_GN_SCRATCH_FLOATS(B, groups) (2 * (groups) * ((B) + 4 * 148 + 2 * (B)) + (B) + 64)
+#define GLG_GN_SCRATCH_FLOATS(B, groups) (128 + 2 * (groups) * (8 * 148 + (B)))
 int glg_groupnorm(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma, const float* beta,
                   float* stats, int32_t B, int32_t HW, int32_t C, int32_t groups, float eps, int32_t silu,
                   void* stream);

@@ -119,6 +119,7 @@ class UNetModel(ParamNode):
     def load_state_dict(self, state_dict, strict=True, **kw):
         out = super().load_state_dict(state_dict, strict=strict, **kw)
         self._engine_stale = True
+        self._masters_valid = True
         self._forget_first_conv_swap()
         return out
 
@@ -153,9 +154,26 @@ class UNetModel(ParamNode):
             self._engine = Engine(self.cfg, CudaOps(dev))
             self._engine_stale = True
         if self._engine_stale:
+            if not getattr(self, "_masters_valid", True):
+                raise RuntimeError("this rank received only the packed weights (broadcast_packed_weights); its fp32 module "
+                                   "parameters are not authoritative and cannot be re-packed - load a state dict first")
             self._engine.load_state_dict(self.state_dict())
             self._engine_stale = False
         return self._engine
+
+    def broadcast_packed_weights(self, src=0):
+        """Multi-GPU init (one process per GPU): rank `src` holds the checkpoint; every other rank receives the engine's
+        packed bf16 arena in a few large NCCL broadcasts (half the bytes of the fp32 masters, no re-packing on the
+        receivers).  The receivers' nn.Parameters keep their construction-time values and are marked non-authoritative.
+        Returns the bytes sent (0 when torch.distributed is not initialised)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return 0
+        eng = self.engine()                       # src: packs the real weights; others: packs placeholders (allocates slots)
+        sent = eng.broadcast_packed(src)
+        if dist.get_rank() != src:
+            self._masters_valid = False
+        return sent
 
     def restore_first_conv_from_SD(self):
         """reference openaimodel.py:400-413: swap input_blocks[0][0] for SD's 4->C conv, read from the

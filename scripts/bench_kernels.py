@@ -11,7 +11,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from gligen_b200.ops import CudaOps  # noqa: E402
+from gligen_b200.ops import CudaOps, gn_scratch_floats  # noqa: E402
 
 dev = "cuda:0"
 ops = CudaOps(dev)
@@ -49,27 +49,35 @@ for (d, T, G, heads) in ((40, 4096, 30, 8), (80, 1024, 30, 8), (160, 256, 30, 8)
     qkv = rnd(Bt, T + G, 3 * C)
     out = torch.empty(Bt, T, C, device=dev, dtype=torch.bfloat16)
     kv = rnd(Bt, 77, 2 * C)
-    for mode, mname in ((0, "auto"), (1, "mma_sync"), (2, "tcgen05")):
-        if d > 128 and mode != 0:
-            continue
+    qc = qkv[:, :T, :C].contiguous()
+    for mode, mname in ((0, "auto"), (1, "mma_sync"), (2, "tcgen05"), (3, "short_tc"), (4, "tc2")):
         ops.lib.glg_debug_attn_mode(mode)
-        timeit(f"attn self  d={d} T={T} [{mname}]", lambda: ops.attention(qkv[:, :T, :C], qkv[:, :T, C:2 * C], qkv[:, :T, 2 * C:], out, heads, d),
-               flops=4.0 * Bt * heads * T * T * d)
-        timeit(f"attn fuser d={d} T={T}+{G} [{mname}]", lambda: ops.attention(qkv[:, :T, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], out, heads, d),
-               flops=4.0 * Bt * heads * T * (T + G) * d)
-        timeit(f"attn cross d={d} T={T}x77 [{mname}]", lambda: ops.attention(out, kv[:, :, :C], kv[:, :, C:], qkv[:, :T, :C].contiguous(), heads, d),
-               flops=4.0 * Bt * heads * T * 77 * d)
+        if mode == 4 and d != 40:
+            continue
+        if mode != 3:
+            timeit(f"attn self  d={d} T={T} [{mname}]", lambda: ops.attention(qkv[:, :T, :C], qkv[:, :T, C:2 * C], qkv[:, :T, 2 * C:], out, heads, d),
+                   flops=4.0 * Bt * heads * T * T * d)
+            timeit(f"attn fuser d={d} T={T}+{G} [{mname}]", lambda: ops.attention(qkv[:, :T, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], out, heads, d),
+                   flops=4.0 * Bt * heads * T * (T + G) * d)
+        if mode != 4:
+          timeit(f"attn cross d={d} T={T}x77 [{mname}]", lambda: ops.attention(out, kv[:, :, :C], kv[:, :, C:], qc, heads, d),
+               flops=4.0 * Bt * heads * T * 77 * d, nbytes=2.0 * Bt * T * C * 2)
     ops.lib.glg_debug_attn_mode(0)
 
 # ---------------- GEMMs (token GEMMs of the transformer blocks) ----------------
-for cta2, cname in ((1, "1cta"), (2, "2cta"), (0, "auto")):
+for cta2, bres, epi, cname in ((1, 1, 0, "stream-oldepi"), (1, 1, 1, "stream"), (1, 2, 1, "resident"), (2, 1, 1, "2cta"), (0, 0, 1, "auto")):
   ops.lib.glg_debug_gemm_cta2(cta2)
+  ops.lib.glg_debug_gemm_bres(bres)
+  ops.lib.glg_debug_gemm_epi(epi)
   for (T, C) in ((4096, 320), (1024, 640), (256, 1280), (64, 1280)):
       M = Bt * T
       x = rnd(M, C)
       res = rnd(M, C)
       bias = torch.randn(C, device=dev)
-      for (nm, N, K, kw) in (("qkv", 3 * C, C, {}), ("proj/out +bias+res", C, C, dict(bias=bias, residual=res)), ("ff2 +bias+res", C, 4 * C, dict(bias=bias, residual=res))):
+      xst = torch.zeros(C // 32, M, 2, device=dev)
+      cs = torch.randn(3 * C, device=dev)
+      for (nm, N, K, kw) in (("qkv", 3 * C, C, {}), ("qkv +lnfold", 3 * C, C, dict(ln=(xst, cs, 1e-5), bias=cs)), ("proj/out +bias+res", C, C, dict(bias=bias, residual=res)),
+                             ("out +bias+res+stats", C, C, dict(bias=bias, residual=res, stats_out=xst)), ("ff2 +bias+res", C, 4 * C, dict(bias=bias, residual=res))):
           a = rnd(M, K)
           w = rnd(N, K, scale=K ** -0.5)
           o = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
@@ -80,6 +88,8 @@ for cta2, cname in ((1, "1cta"), (2, "2cta"), (0, "auto")):
       timeit(f"gemm[{cname}] {'ff1 geglu':20s} M={M} N={8*C} K={C}", lambda: ops.gemm(x, w1, o1, bias=b1, geglu=True), flops=2.0 * M * 8 * C * C, nbytes=2.0 * (M * C + 8 * C * C + M * 4 * C))
 
 ops.lib.glg_debug_gemm_cta2(0)
+ops.lib.glg_debug_gemm_bres(0)
+ops.lib.glg_debug_gemm_epi(-1)
 for cta2, cname in ((1, "1cta"), (2, "2cta")):
     ops.lib.glg_debug_gemm_cta2(cta2)
     for (M, N, K) in ((4096, 4096, 4096), (8192, 8192, 8192)):
@@ -100,7 +110,7 @@ for (H, Cin, Cout) in ((64, 320, 320), (64, 960, 320), (64, 640, 320), (64, 640,
     ops.lib.glg_debug_gemm_cta2(0)
 
 # ---------------- norms ----------------
-stats = torch.zeros(2 * 32 * (Bt + 4 * 148 + 2 * Bt) + Bt + 64, device=dev)
+stats = torch.zeros(gn_scratch_floats(Bt), device=dev)
 for (HW, C) in ((4096, 320), (4096, 960), (4096, 640), (1024, 640), (1024, 1920), (256, 1280), (256, 2560), (64, 2560)):
     x = rnd(Bt, HW, C)
     y = torch.empty_like(x)

@@ -46,7 +46,7 @@ class RefOps:
         M = y.shape[0]
         if ln is not None:       # LayerNorm fold: rstd * (x W'^T - mu * colsum)   (gamma in W', beta in the bias)
             st, colsum, eps = ln
-            s1, s2 = st[:, :, 0].sum(1), st[:, :, 1].sum(1)
+            s1, s2 = st[:, :, 0].sum(0), st[:, :, 1].sum(0)          # slot-major [S, M, 2]
             mu = s1 / K
             rstd = torch.rsqrt((s2 / K - mu * mu).clamp_min(0) + eps)
             y = rstd[:, None] * (y - mu[:, None] * colsum.float()[None])
@@ -72,8 +72,8 @@ class RefOps:
         out.copy_(stored)
         if stats_out is not None:
             sv = stored.float().reshape(M, -1, 32)               # one partial per 32-column chunk
-            stats_out[:, :, 0] = sv.sum(2)
-            stats_out[:, :, 1] = (sv * sv).sum(2)
+            stats_out[:, :, 0] = sv.sum(2).t()                       # slot-major [S, M, 2]
+            stats_out[:, :, 1] = (sv * sv).sum(2).t()
 
     def attention(self, q, k, v, out, heads, d_head):
         self.launches += 1

@@ -1,5 +1,6 @@
-"""bench.py contract pieces that run without a GPU: the reference arm (oracle port on the host cores) prints one JSON
-line with the keys the driver reads; the product arm refuses to run without CUDA (no CPU fallback)."""
+"""bench.py contract pieces that run without a GPU: the reference arm (the real reference PLMSSampler + UNetModel from
+oracle/_ref or /root/reference on the host cores; the oracle port only when neither exists) prints one JSON line with the
+keys the driver reads; the product arm refuses to run without CUDA (no CPU fallback)."""
 import json
 import os
 import subprocess
@@ -19,7 +20,10 @@ def test_reference_arm_line():
     assert line["value"] > 0 and line["e2e"]["value"] == line["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    have_ref = os.path.isdir("/root/reference") or os.path.exists(os.path.join(ROOT, "oracle", "_ref", "gligen_reference.zip"))
+    assert cb["kind"] == ("reference" if have_ref else "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    if have_ref:
+        assert "PLMSSampler.sample" in cb["sample"] and line["config"]["reference_batch"] >= 1
     assert "workload" in line["config"] and "model" not in line["config"]
 
 

@@ -1,0 +1,69 @@
+"""Shard-equivalence on hardware: a 2-GPU run (one process per GPU, NCCL; weights broadcast once as the
+packed bf16 arena; the global batch sharded contiguously; NO collective on the per-step path) produces, row for row,
+the latents of the 1-GPU run of the same global batch - within a stated tolerance, because the per-rank batch changes
+M and with it the GEMM tile / split-K choices (same bf16 math, different fp32 summation order).
+
+Needs 2 GPUs (`gpurun --gpus 2`); skipped on a single-GPU box."""
+import os
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+REL, MAX_REL = 2e-2, 8e-2          # 3 sampler steps (8 UNet passes) of re-ordered bf16 arithmetic; measured values are printed
+
+
+def _worker(rank, world, port, name, B_total, S, out_path):
+    import torch.distributed as dist
+    from functools import partial
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", device_id=dev)
+    from gligen_b200 import synth
+    from gligen_b200.dist import gather_latents, shard_batch
+    from gligen_b200.pipeline import alpha_generator, build_model, sampler_inputs, set_alpha_scale, to_device
+    from gligen_b200.spec import synthetic_state_dict
+    from ldm.models.diffusion.ldm import LatentDiffusion
+    from ldm.models.diffusion.plms import PLMSSampler
+    cfg, model = build_model(name, dev, load_weights=False)
+    if rank == 0:
+        model.load_state_dict(synthetic_state_dict(cfg, seed=0))
+    sent = model.broadcast_packed_weights(src=0)
+    assert sent > 0
+    diffusion = LatentDiffusion(linear_start=0.00085, linear_end=0.012, timesteps=1000).to(dev)
+
+    def sample(inp):
+        sampler = PLMSSampler(diffusion, model, alpha_generator_func=partial(alpha_generator, type=[1, 0, 0]), set_alpha_scale=set_alpha_scale)
+        t = {k: v.to(dev) for k, v in inp.items() if isinstance(v, torch.Tensor)}
+        input, mask, x0 = sampler_inputs(cfg, model, t, to_device(inp["batch"], dev))
+        b = t["x"].shape[0]
+        return sampler.sample(S=S, shape=(b, cfg.in_channels, cfg.image_size, cfg.image_size), input=input, uc=t["uc"], guidance_scale=7.5, mask=mask, x0=x0)
+
+    full = synth.make_inputs(cfg, B_total, 30, seed=5)              # drawn for the GLOBAL batch, then sliced
+    mine = shard_batch(full, rank, world)
+    lat = gather_latents(sample(mine))
+    if rank == 0:
+        single = sample(full)                                       # the same global batch on one GPU
+        torch.save({"sharded": lat.cpu(), "single": single.cpu(), "bytes_broadcast": sent}, out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("name,B_total,S", [("tiny", 4, 4), ("sd14_box_text", 4, 3)])
+def test_two_gpu_shards_equal_single_gpu(name, B_total, S, tmp_path):
+    import torch.multiprocessing as mp
+    out = os.path.join(str(tmp_path), "out.pt")
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, name, B_total, S, out), nprocs=2, join=True)
+    r = torch.load(out)
+    d = (r["sharded"] - r["single"]).float()
+    rel = (d.norm() / r["single"].float().norm()).item()
+    mx = d.abs().max().item() / r["single"].abs().max().item()
+    print(f"\n2-GPU vs 1-GPU {name} B={B_total} PLMS S={S}: rel_l2={rel:.3e} max_rel={mx:.3e}; packed weights broadcast: {r['bytes_broadcast'] / 1e9:.2f} GB")
+    assert rel <= REL and mx <= MAX_REL, (rel, mx)

@@ -21,48 +21,13 @@ from gligen_b200.spec import NAMED_CONFIGS, synthetic_state_dict
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
-TOKENIZER = {
-    "text": ("ldm.modules.diffusionmodules.text_grounding_net.PositionNet", lambda c: dict(in_dim=c.tok_in_dim, out_dim=c.tok_out_dim)),
-    "text_image": ("ldm.modules.diffusionmodules.text_image_grounding_net.PositionNet", lambda c: dict(in_dim=c.tok_in_dim, out_dim=c.tok_out_dim)),
-    "keypoint": ("ldm.modules.diffusionmodules.keypoint_grounding_net.PositionNet", lambda c: dict(max_persons_per_image=c.max_persons, out_dim=c.tok_out_dim)),
-}
-GIN = {"text": "text_grounding_tokinzer_input", "text_image": "text_image_grounding_tokinzer_input", "keypoint": "keypoint_grounding_tokinzer_input"}
+from gligen_b200.pipeline import alpha_generator, build_model as _build_model, set_alpha_scale  # noqa: E402  (gligen_inference glue)
 
 
 def build_model(name):
     """Exactly what gligen_inference.load_ckpt does: instantiate_from_config(config['model']).to(device).eval()
-    + load_state_dict (gligen_inference.py:70-86), with the yaml params as a plain dict."""
-    from ldm.util import instantiate_from_config
-    import importlib
-    cfg = NAMED_CONFIGS[name]
-    tgt, par = TOKENIZER[cfg.tokenizer]
-    config = dict(target="ldm.modules.diffusionmodules.openaimodel.UNetModel", params=dict(
-        image_size=cfg.image_size, in_channels=cfg.in_channels, out_channels=cfg.out_channels, model_channels=cfg.model_channels,
-        attention_resolutions=list(cfg.attention_resolutions), num_res_blocks=cfg.num_res_blocks, channel_mult=list(cfg.channel_mult),
-        num_heads=cfg.num_heads, transformer_depth=1, context_dim=cfg.context_dim, fuser_type="gatedSA", use_checkpoint=True,
-        inpaint_mode=cfg.inpaint_mode, grounding_tokenizer=dict(target=tgt, params=par(cfg))))
-    model = instantiate_from_config(config).to(DEV).eval()
-    model.load_state_dict(synthetic_state_dict(cfg, seed=0))
-    model.grounding_tokenizer_input = importlib.import_module(f"grounding_input.{GIN[cfg.tokenizer]}").GroundingNetInput()
-    return cfg, model
-
-
-def set_alpha_scale(model, alpha_scale):
-    """gligen_inference.py:24-28, verbatim semantics (type identity on the class exported by ldm.modules.attention)."""
-    from ldm.modules.attention import GatedCrossAttentionDense, GatedSelfAttentionDense
-    for module in model.modules():
-        if type(module) == GatedCrossAttentionDense or type(module) == GatedSelfAttentionDense:
-            module.scale = alpha_scale
-
-
-def alpha_generator(length, type=None):
-    """gligen_inference.py:31-66."""
-    if type is None:
-        type = [1, 0, 0]
-    s0, s1 = int(type[0] * length), int(type[1] * length)
-    s2 = length - s0 - s1
-    decay = list(np.arange(start=0, stop=1, step=1 / s1)[::-1]) if s1 != 0 else []
-    return [1] * s0 + decay + [0] * s2
+    + load_state_dict (gligen_inference.py:70-86), with the yaml params as a plain dict (gligen_b200/pipeline.py)."""
+    return _build_model(name, DEV)
 
 
 def to_dev(d):
@@ -165,6 +130,22 @@ def test_sampling_sd14_config1():
     """BASELINE config 1 (1x4x64x64, 2 DDIM steps, 2 box+text tokens) and PLMS S=4 with scheduled sampling
     [0.5,0,0.5] incl. the first-conv swap, full-size model."""
     run_sampling("sd14_box_text", "sd14_box_text_B1_G2.pt")
+
+
+@pytest.mark.parametrize("name,gold_file", [("sd14_box_text_image", "sd14_box_text_image_B1_G30.pt"),      # BASELINE config 3: 30 objects -> 60 tokens
+                                            ("sd14_keypoint", "sd14_keypoint_B1_G136.pt"),                # config 5: 8 x 17 = 136 tokens
+                                            ("sd14_inpaint_box_text", "sd14_inpaint_box_text_B1_G30.pt")])  # config 4: 9-channel first conv
+def test_forward_sd14_other_tokenizers(name, gold_file):
+    """Full-size eps against the reference for the grounding variants of BASELINE configs 3, 4 and 5 (text+image
+    PositionNet text_image_grounding_net.py:41-65, keypoint keypoint_grounding_net.py:34-58, inpainting input
+    openaimodel.py:444-447)."""
+    run_forwards(name, gold_file)
+
+
+def test_sampling_sd14_inpaint():
+    """BASELINE config 4's loop at full size: PLMS with scheduled sampling [0.3,0,0.7] and the per-step inpaint blend
+    (plms.py:96-100), DDIM S=2; the q_sample noise is drawn from the CPU generator like the golden run."""
+    run_sampling("sd14_inpaint_box_text", "sd14_inpaint_box_text_B1_G30.pt")
 
 
 def test_scale_zero_equals_fuser_removed():

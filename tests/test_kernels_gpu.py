@@ -8,6 +8,7 @@ import torch
 
 from conftest import assert_close
 from ref_ops import RefOps
+from gligen_b200.ops import gn_scratch_floats
 
 pytestmark = pytest.mark.gpu
 
@@ -90,15 +91,60 @@ def test_gemm(ops, ref, M, N, K, fl, force_bn, cta2):
         assert big[:, :64].abs().max().item() == 0.0, "wrote outside the output slice"
 
 
+@pytest.mark.parametrize("M,N,K,fl", GEMM_CASES + [(32768, 320, 320, dict(bias=True, residual=True)), (9000, 1920, 640, dict(bias=True)),
+                                                   (20000, 2560, 320, dict(geglu=True)), (130, 320, 320, dict(bias=True))])
+@pytest.mark.parametrize("force_bn", [0, 64, 128, 160, 256])
+def test_gemm_weights_resident(ops, ref, M, N, K, fl, force_bn):
+    """B-resident mode forced wherever the weight tile fits in shared memory (one n-tile per CTA for its lifetime, the
+    weight tile loaded once, only A streams): same results as the torch statement, incl. CTAs that own no m-block."""
+    if force_bn and (N % force_bn or fl.get("geglu")):
+        pytest.skip("BN does not divide N")
+    if fl.get("fp32") or fl.get("strided") or fl.get("rowbias"):
+        pytest.skip("covered by the streaming-mode test (same epilogue code)")
+    import ctypes as C
+    pick = (C.c_int32 * 3)()
+    ops.lib.glg_debug_force_bn(force_bn)
+    ops.lib.glg_debug_gemm_cta2(1)
+    ops.lib.glg_debug_gemm_bres(2)
+    try:
+        ops.lib.glg_debug_pick_tile(M, N, K, 1 if fl.get("geglu") else 0, 0, 0, 0, pick)
+        if not (pick[1] >> 8):
+            pytest.skip("weight tile does not fit beside three A stages")
+        a = rnd(M, K)
+        w = rnd(N, K, scale=K ** -0.5, seed=1)
+        geglu = fl.get("geglu", False)
+        No = N // 2 if geglu else N
+        bias = rnd(N, seed=2, dtype=torch.float32) if (fl.get("bias") or geglu) else None
+        gate = torch.tensor([0.37], device="cuda:0") if fl.get("gate") else None
+        residual = rnd(M, No, seed=4) if fl.get("residual") else None
+        out, out_r = torch.zeros(M, No, device="cuda:0", dtype=torch.bfloat16), torch.zeros(M, No, device="cuda:0", dtype=torch.bfloat16)
+        kw = dict(bias=bias, act=1 if fl.get("act") else 0, gate=gate, residual=residual, geglu=geglu)
+        ops.gemm(a, w, out, **kw)
+        torch.cuda.synchronize()
+        out2 = torch.zeros_like(out)
+        ops.gemm(a, w, out2, **kw)
+        torch.cuda.synchronize()
+    finally:
+        ops.lib.glg_debug_force_bn(0)
+        ops.lib.glg_debug_gemm_cta2(0)
+        ops.lib.glg_debug_gemm_bres(0)
+    ref.gemm(a, w, out_r, **kw)
+    assert_close(out, out_r, what=f"B-resident gemm {M}x{N}x{K} {fl} bn={force_bn}")
+    assert torch.equal(out, out2)
+
+
 @pytest.mark.parametrize("M,N,K,geglu", [(4096, 960, 320, False), (1000, 1920, 640, False), (300, 1280, 1280, False),
                                          (4096, 2560, 320, True), (520, 1024, 128, True)])
-@pytest.mark.parametrize("cta2", [1, 2])
-def test_gemm_layernorm_fold(ops, ref, M, N, K, geglu, cta2):
+@pytest.mark.parametrize("cta2,bres", [(1, 1), (2, 1), (1, 2)])
+def test_gemm_layernorm_fold(ops, ref, M, N, K, geglu, cta2, bres):
+    """bres: 1 = streaming tiles only, 2 = weights-resident tiles wherever they fit."""
     ops.lib.glg_debug_gemm_cta2(cta2)
+    ops.lib.glg_debug_gemm_bres(bres)
     try:
         _ln_fold_case(ops, ref, M, N, K, geglu)
     finally:
         ops.lib.glg_debug_gemm_cta2(0)
+        ops.lib.glg_debug_gemm_bres(0)
 
 
 def _ln_fold_case(ops, ref, M, N, K, geglu):
@@ -109,12 +155,12 @@ def _ln_fold_case(ops, ref, M, N, K, geglu):
     res = rnd(M, K, seed=2) * 2 + 0.7                      # non-zero row means: exercises the mu * colsum cancellation
     x = torch.zeros(M, K, device="cuda:0", dtype=torch.bfloat16)
     slots = K // 32
-    st = torch.full((M, slots, 2), 7.0, device="cuda:0")   # poisoned: unused slots must be zeroed by the kernel
+    st = torch.full((slots, M, 2), 7.0, device="cuda:0")   # slot-major; poisoned: every slot must be written by the kernel
     ops.gemm(a0, w0, x, residual=res, stats_out=st)
     torch.cuda.synchronize()
     xf = x.float()
-    assert_close(st[:, :, 0].sum(1), xf.sum(1), rel=1e-5, max_rel=1e-4, what="row sums")
-    assert_close(st[:, :, 1].sum(1), (xf * xf).sum(1), rel=1e-5, max_rel=1e-4, what="row sums of squares")
+    assert_close(st[:, :, 0].sum(0), xf.sum(1), rel=1e-5, max_rel=1e-4, what="row sums")
+    assert_close(st[:, :, 1].sum(0), (xf * xf).sum(1), rel=1e-5, max_rel=1e-4, what="row sums of squares")
     gamma = 1 + 0.2 * rnd(K, seed=3, dtype=torch.float32)
     beta = 0.2 * rnd(K, seed=4, dtype=torch.float32)
     w = rnd(N, K, scale=K ** -0.5, seed=5, dtype=torch.float32)
@@ -243,18 +289,24 @@ ATTN_CASES = [
     (2, 8, 40, 300, 257, "plain"),         # ragged query tile, 5 key tiles (last: 1 key)
     (1, 8, 24, 512, 1000, "plain"),
     (1, 4, 64, 257, 384, "plain"),
+    (2, 8, 40, 200, 64, "plain"),          # one key tile: the second softmax warpgroup of the two-warpgroup kernel sees none
+    (1, 8, 40, 384, 129, "plain"),         # three key tiles (2 + 1), last one a single key
+    (1, 4, 56, 130, 640, "plain"),
 ]
 
 
 @pytest.mark.parametrize("B,heads,d,Lq,Lk,mode", ATTN_CASES)
-@pytest.mark.parametrize("path", ["auto", "mma_sync", "tcgen05", "tcgen05_sum"])
+@pytest.mark.parametrize("path", ["auto", "mma_sync", "tcgen05", "tcgen05_sum", "short_tc", "tc2"])
 def test_attention(ops, ref, B, heads, d, Lq, Lk, mode, path):
-    """auto: tcgen05 kernel (d_head <= 128, > 128 keys), K/V-resident mma.sync kernel (<= 128 keys: text context),
-    streaming mma.sync kernel (d_head > 128).  Row sums come from a ones column of V when d_head % 16 != 0.
-    The other paths force mma.sync / tcgen05 (also for short key sets) / tcgen05 with the softmax-side row sum."""
-    if path != "auto" and d > 128:
-        pytest.skip("same kernel as auto")
-    if path == "tcgen05" and Lk > 128:
+    """auto: streamed tcgen05 flash kernel (> 128 keys, every d_head <= 160), short-key tcgen05 kernel (<= 128 keys: the
+    text context).  Row sums come from a ones column of V when d_head % 16 != 0 (streamed kernel).
+    The other paths force the legacy mma.sync kernel / the streamed tcgen05 kernel (also for short key sets) / the
+    streamed kernel with the softmax-side row sum."""
+    if path == "tc2" and (d % 16 == 0 or d > 64):
+        pytest.skip("two-warpgroup kernel: d_head < 64 with a spare column for the row sums")
+    if path == "short_tc" and (Lk > 128 or d > 128 and Lk > 80):
+        pytest.skip("short-key kernel: all keys in one tile")
+    if path == "short_tc" and Lk <= 128:
         pytest.skip("same kernel as auto")
     if path == "tcgen05_sum" and d % 16 == 0:
         pytest.skip("same kernel as tcgen05 / auto")
@@ -273,7 +325,7 @@ def test_attention(ops, ref, B, heads, d, Lq, Lk, mode, path):
         q, k, v = rnd(B, Lq, C), rnd(B, Lk, C, seed=1), rnd(B, Lk, C, seed=2)
     out = torch.zeros(B, Lq, C, device="cuda:0", dtype=torch.bfloat16)
     out_r = torch.zeros_like(out)
-    ops.lib.glg_debug_attn_mode({"auto": 0, "mma_sync": 1, "tcgen05": 2, "tcgen05_sum": 2}[path])
+    ops.lib.glg_debug_attn_mode({"auto": 0, "mma_sync": 1, "tcgen05": 2, "tcgen05_sum": 2, "short_tc": 3, "tc2": 4}[path])
     ops.lib.glg_debug_attn_tc_variant(3 if path == "tcgen05_sum" else 0)
     try:
         ops.attention(q, k, v, out, heads, d)
@@ -294,7 +346,7 @@ def test_groupnorm(ops, ref, B, HW, C, ld, eps, silu):
     x = big[:, :, ld - C:]
     gamma = 1 + 0.1 * rnd(C, seed=1, dtype=torch.float32)
     beta = 0.1 * rnd(C, seed=2, dtype=torch.float32)
-    stats = torch.zeros(2 * 32 * (B + 4 * 148 + 2 * B) + B + 64, device="cuda:0")
+    stats = torch.zeros(gn_scratch_floats(B), device="cuda:0")
     y, y_r = torch.zeros(B, HW, C, device="cuda:0", dtype=torch.bfloat16), torch.zeros(B, HW, C, device="cuda:0", dtype=torch.bfloat16)
     ops.groupnorm(x, y, gamma, beta, stats, 32, eps, silu)
     torch.cuda.synchronize()
@@ -303,6 +355,33 @@ def test_groupnorm(ops, ref, B, HW, C, ld, eps, silu):
     y2 = torch.zeros_like(y)
     ops.groupnorm(x, y2, gamma, beta, stats, 32, eps, silu)
     assert torch.equal(y, y2), "groupnorm must be bit-reproducible"
+
+
+@pytest.mark.parametrize("B,HW,C,mean", [(2, 4096, 320, 40.0), (8, 4096, 320, -25.0), (2, 1024, 1920, 60.0), (16, 1024, 640, 10.0),
+                                         (3, 256, 1280, 50.0), (2, 64, 2560, -80.0), (64, 256, 64, 30.0)])
+def test_groupnorm_large_mean(ops, B, HW, C, mean):
+    """Post-residual streams carry channel groups whose mean is far from 0: |mean| / std up to ~100 here.  The raw
+    E[x^2] - E[x]^2 form loses the variance in fp32 there; the reference's GroupNorm32 (util.py:223-225, F.group_norm in
+    fp32: two-pass) does not.  Checked against torch's fp32 group_norm on the same bf16 input; also covers up to 64
+    samples per call (one barrier counter each) and bit-reproducibility of the in-kernel barrier path."""
+    g = torch.Generator(device="cpu").manual_seed(11)
+    base = torch.randn(B, HW, C, generator=g) * 0.8
+    # per-group offsets around `mean` (groups of C/32 channels), a few channels with their own offset inside a group
+    off = mean * (1.0 + 0.5 * torch.randn(B, 1, 32, generator=g)).repeat_interleave(C // 32, dim=2)
+    off[:, :, ::7] += 3.0
+    x = (base + off).to("cuda:0", torch.bfloat16)
+    gamma = (1 + 0.1 * torch.randn(C, generator=g)).cuda()
+    beta = (0.1 * torch.randn(C, generator=g)).cuda()
+    stats = torch.zeros(gn_scratch_floats(B), device="cuda:0")
+    y = torch.zeros(B, HW, C, device="cuda:0", dtype=torch.bfloat16)
+    ops.groupnorm(x, y, gamma, beta, stats, 32, 1e-5, False)
+    torch.cuda.synchronize()
+    want = torch.nn.functional.group_norm(x.float().transpose(1, 2), 32, gamma, beta, 1e-5).transpose(1, 2)
+    assert_close(y, want, rel=4e-3, max_rel=1e-2, what=f"groupnorm large mean {mean}")     # bf16 output rounding only
+    y2 = torch.zeros_like(y)
+    ops.groupnorm(x, y2, gamma, beta, stats, 32, 1e-5, False)
+    assert torch.equal(y, y2), "groupnorm must be bit-reproducible"
+    assert int(stats[:128].view(torch.int32).abs().sum()) == 0, "barrier counters must re-arm themselves"
 
 
 @pytest.mark.parametrize("B,rows,C", [(2, 4096, 320), (2, 30, 640), (3, 64, 1280), (2, 16, 64), (2, 7, 2048)])
