@@ -347,6 +347,53 @@ __global__ void sampler_update_kernel(const float* __restrict__ x, const float* 
 
 }  // namespace glg
 
+namespace glg {
+// Row softmax of an fp32 score matrix -> bf16 probabilities (sum of a row = 1 before rounding): one CTA per row.
+// Used by the VAE decoder's single-head attention over H*W tokens (model.py:178-202), whose head dim (512) is too wide
+// for the flash kernels' TMEM budget: QK^T and P.V run as glg_gemm, the scores make one round trip through L2.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, long long lds, bf16* __restrict__ p, long long ldp,
+                                                          int cols, float scale_log2) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float red[8];
+  const float* row = s + (long long)blockIdx.x * lds;
+  bf16* out = p + (long long)blockIdx.x * ldp;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row + c));
+    mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  const float ms = mx * scale_log2;
+  float sum = 0.f;
+  for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row + c));
+    sum += exp2f(fmaf(v.x, scale_log2, -ms)) + exp2f(fmaf(v.y, scale_log2, -ms)) + exp2f(fmaf(v.z, scale_log2, -ms)) + exp2f(fmaf(v.w, scale_log2, -ms));
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += red[w];           // fixed order
+  const float inv = 1.0f / tot;
+  for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row + c));
+    uint2 u;
+    u.x = pack_bf16x2(exp2f(fmaf(v.x, scale_log2, -ms)) * inv, exp2f(fmaf(v.y, scale_log2, -ms)) * inv);
+    u.y = pack_bf16x2(exp2f(fmaf(v.z, scale_log2, -ms)) * inv, exp2f(fmaf(v.w, scale_log2, -ms)) * inv);
+    *reinterpret_cast<uint2*>(out + c) = u;
+  }
+}
+}  // namespace glg
+
 using namespace glg;
 #define ST reinterpret_cast<cudaStream_t>(stream)
 
@@ -378,17 +425,27 @@ extern "C" int glg_conv_out(const void* x, int64_t ldx, const float* w, const fl
                             int32_t B, int32_t H, int32_t Wd, int32_t Cin, int32_t Cout, void* stream) {
   if (Cin % 8 || ldx % 8) return set_error("glg_conv_out: Cin and ldx must be multiples of 8");
   const long long pix = (long long)B * H * Wd;
-  if (Wd % 8 == 0 && Cout == 4) {
-    launch_k(conv_out_px8_kernel<4>, dim3(blocks_for(pix / 8, 8)), dim3(256), 0, ST, 1, (const bf16*)x, ldx, w, bias, out, B, H, Wd, Cin);
+  if (Wd % 8 == 0 && (Cout == 4 || Cout == 3)) {
+    if (Cout == 4) launch_k(conv_out_px8_kernel<4>, dim3(blocks_for(pix / 8, 8)), dim3(256), 0, ST, 1, (const bf16*)x, ldx, w, bias, out, B, H, Wd, Cin);
+    else launch_k(conv_out_px8_kernel<3>, dim3(blocks_for(pix / 8, 8)), dim3(256), 0, ST, 1, (const bf16*)x, ldx, w, bias, out, B, H, Wd, Cin);
     count_launch();
     return check_launch("conv_out launch");
   }
   const unsigned grid = blocks_for(pix, 8);
   if (Cout == 4) launch_k(conv_out_kernel<4>, dim3(grid), dim3(256), 0, ST, 1, (const bf16*)x, ldx, w, bias, out, B, H, Wd, Cin);
   else if (Cout == 8) launch_k(conv_out_kernel<8>, dim3(grid), dim3(256), 0, ST, 1, (const bf16*)x, ldx, w, bias, out, B, H, Wd, Cin);
-  else return set_error("glg_conv_out: Cout must be 4 or 8");
+  else if (Cout == 3) launch_k(conv_out_kernel<3>, dim3(grid), dim3(256), 0, ST, 1, (const bf16*)x, ldx, w, bias, out, B, H, Wd, Cin);
+  else return set_error("glg_conv_out: Cout must be 3, 4 or 8");
   count_launch();
   return check_launch("conv_out launch");
+}
+
+extern "C" int glg_softmax_rows(const float* s, int64_t lds, void* p, int64_t ldp, int64_t rows, int32_t cols, float scale, void* stream) {
+  if (cols <= 0 || cols % 4 || ldp % 2 || lds % 4) return set_error("glg_softmax_rows: cols % 4, lds % 4, ldp % 2 required");
+  if (rows <= 0) return 0;
+  launch_k(softmax_rows_kernel, dim3((unsigned)rows), dim3(256), 0, ST, 1, s, (long long)lds, (bf16*)p, (long long)ldp, cols, scale * 1.4426950408889634f);
+  count_launch();
+  return check_launch("softmax_rows launch");
 }
 
 extern "C" int glg_upsample2x(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t B, int32_t H, int32_t Wd, int32_t C, void* stream) {

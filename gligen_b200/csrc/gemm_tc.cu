@@ -2,13 +2,15 @@
 //
 //   out[M,N] = epilogue( A[M,K] . W[N,K]^T )           bf16 operands, fp32 accumulation in TMEM
 //
-// Persistent, warp-specialised, 10 warps per CTA:
-//   warp 0 lane 0 : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
-//   warp 1 lane 0 : MMA issuer    (tcgen05.mma, K=16 per instruction, accumulator double-buffered in TMEM)
-//   warps 2..9    : epilogue      (tcgen05.ld 32x32b -> registers -> LayerNorm fold / bias / time-embedding row
-//                                  bias / SiLU / tanh-gate / residual / GEGLU -> global); two warps per TMEM lane
-//                                  quarter, each taking half of the tile's 32-column chunks; residual rows and
-//                                  LayerNorm statistics are prefetched BEFORE the accumulator is ready.
+// Persistent, warp-specialised, 20 warps per CTA:
+//   warp 0        : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1        : MMA issuer    (tcgen05.mma, K=16 per instruction, up to 4 accumulator stages in TMEM)
+//   warps 2..3    : idle (keep the epilogue warps' index aligned with the TMEM lane quarters)
+//   warps 4..19   : epilogue      (tcgen05.ld 32x32b -> registers -> LayerNorm fold / bias / time-embedding row
+//                                  bias / SiLU / tanh-gate / residual / GEGLU -> bf16 -> 64B-swizzled smem -> TMA store);
+//                                  four warps per TMEM lane quarter, each taking every fourth 32-column chunk of the
+//                                  tile; residual chunks arrive by TMA, LayerNorm statistics are prefetched BEFORE the
+//                                  accumulator is ready.
 //
 // Two instantiations of the same code:
 //   CTA2 = false : one CTA per tile, tcgen05.mma.cta_group::1, tile 128 x BN.
@@ -167,13 +169,6 @@ template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm vol
 __device__ __forceinline__ uint32_t sw64_addr(uint32_t buf, int row, int piece) {
   return buf + (uint32_t)row * 64u + ((uint32_t)(piece ^ ((row >> 1) & 3)) << 4);
 }
-struct EpiWarp {              // per-warp epilogue staging state
-  uint32_t out_stage;         // 2 x 2 KB
-  uint32_t res_stage;         // 2 x 2 KB
-  uint32_t res_bar;           // 2 mbarriers
-  uint32_t res_phase;         // bit i: phase of res_bar[i]
-  int out_buf, res_buf;       // next buffer to use
-};
 
 // 256-bit global accesses (sm_100: STG/LDG.256): a thread's 64-byte bf16 row chunk leaves as two full 32-byte
 // sectors instead of four half-sector writes (which doubled the L1->L2 crossbar write traffic).
@@ -217,218 +212,212 @@ __device__ __forceinline__ void load_res_chunk(const bf16* src, uint4 (&r)[4], b
   }
 }
 
-// ---- epilogue of one 128-row x BN accumulator for the calling warp (lane quarter q, chunk half `half`) -----
-// res_pre: the first residual chunk, fetched before the accumulator became ready (latency hidden behind the MMA).
-// stage one packed [32 rows x 32 cols] chunk of this warp and hand it to the TMA (row0 = first row of the warp's slab)
-__device__ __forceinline__ void epi_tma_store(const GemmKParams& p, const CUtensorMap* tmOut, EpiWarp& ew, const uint32_t (&pk)[16],
-                                              int lane, int row0, int col0) {
-  if (lane == 0) tma_store_wait_read<1>();            // the buffer written two chunks ago has been read out
-  __syncwarp();
-  const uint32_t buf = ew.out_stage + (uint32_t)ew.out_buf * 2048u;
+// ---- epilogue of one 128-row x BN accumulator for the calling warp ------------------------------------------------
+// 16 epilogue warps: warp -> (TMEM lane quarter q = warp & 3, column group grp = 0..3); a warp handles the 32-column
+// chunks c = grp, grp + 4, ... of the tile, each as two 16-column halves (register budget: 640 threads x <= 102 regs).
+// Twice the warps per scheduler of the 8-warp layout: ncu showed the 8 warps latency-bound (8 cycles per issued
+// instruction, ~650 instructions per chunk, issue slots 30 % busy) and the short-K GEMMs bound by exactly that.
+struct EpiWarp {              // per-warp epilogue staging state (single-buffered: a warp owns <= 2 chunks per tile)
+  uint32_t out_stage;         // 2 KB: [32 rows][64 B], 64B-swizzled
+  uint32_t res_stage;         // 2 KB
+  uint32_t res_bar;           // mbarrier of the residual TMA load
+  uint32_t res_phase;
+};
+
+__device__ __forceinline__ void epi_res_issue(const CUtensorMap* tmRes, EpiWarp& ew, int lane, int row0, int col0) {
+  if (lane == 0) {
+    mbar_arrive_expect_tx(ew.res_bar, 2048);
+    tma_load_2d(ew.res_stage, tmRes, ew.res_bar, col0, row0);
+  }
+}
+// 8 bf16 pairs (columns [16 h, 16 h + 16) of this lane's row) of the staged residual chunk
+__device__ __forceinline__ void epi_res_half(const EpiWarp& ew, int lane, int h, uint4 (&r)[2]) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw64_addr(buf, lane, j)), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
+  for (int j = 0; j < 2; ++j)
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[j].x), "=r"(r[j].y), "=r"(r[j].z), "=r"(r[j].w)
+                 : "r"(sw64_addr(ew.res_stage, lane, 2 * h + j)) : "memory");
+}
+__device__ __forceinline__ void epi_stage_half(const EpiWarp& ew, int lane, int h, const uint32_t (&pk)[8]) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sw64_addr(ew.out_stage, lane, 2 * h + j)), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
                  "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
+}
+__device__ __forceinline__ void epi_tma_store(const GemmKParams& p, const CUtensorMap* tmOut, const EpiWarp& ew, int lane, int row0, int col0) {
   fence_proxy_async();                                // generic-proxy writes -> visible to the TMA (async proxy)
   __syncwarp();
   if (lane == 0) {
-    if (p.tma_out == 3) tma_store_3d(tmOut, buf, col0, row0 % p.orpb, row0 / p.orpb);
-    else tma_store_2d(tmOut, buf, col0, row0);
+    if (p.tma_out == 3) tma_store_3d(tmOut, ew.out_stage, col0, row0 % p.orpb, row0 / p.orpb);
+    else tma_store_2d(tmOut, ew.out_stage, col0, row0);
     tma_store_commit();
   }
-  ew.out_buf ^= 1;
 }
-// residual chunk (col0) of this warp's slab -> staging buffer ew.res_buf (arrives on its mbarrier)
-__device__ __forceinline__ void epi_res_issue(const CUtensorMap* tmRes, EpiWarp& ew, int lane, int row0, int col0) {
-  if (lane == 0) {
-    const uint32_t bar = ew.res_bar + 8u * ew.res_buf;
-    mbar_arrive_expect_tx(bar, 2048);
-    tma_load_2d(ew.res_stage + (uint32_t)ew.res_buf * 2048u, tmRes, bar, col0, row0);
-  }
-  ew.res_buf ^= 1;
-}
-__device__ __forceinline__ void epi_res_take(EpiWarp& ew, int buf, int lane, uint4 (&r)[4]) {
-  mbar_wait(ew.res_bar + 8u * buf, (ew.res_phase >> buf) & 1u);
-  ew.res_phase ^= 1u << buf;
-  const uint32_t b = ew.res_stage + (uint32_t)buf * 2048u;
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[j].x), "=r"(r[j].y), "=r"(r[j].z), "=r"(r[j].w) : "r"(sw64_addr(b, lane, j)) : "memory");
-  __syncwarp();                                       // all lanes hold their rows: the buffer may be refilled
-}
+__device__ __forceinline__ void add4(float (&v)[16], int j, const float4 t) { v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
 
 template <int BN, bool GEGLU>
-__device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t taddr, int row, int n_blk, int half, float gate,
-                                              float ln_mu, float ln_rstd, uint4 (&res_pre)[4],
-                                              const CUtensorMap* tmOut, const CUtensorMap* tmRes, EpiWarp& ew, int lane) {
+__device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t taddr, int row, int n_blk, int grp, float gate,
+                                              float ln_mu, float ln_rstd, const CUtensorMap* tmOut, const CUtensorMap* tmRes,
+                                              EpiWarp& ew, int lane) {
   const bool row_ok = row < p.M;
   const int row0 = row - lane;                        // first row of this warp's 32-row slab
   const size_t out_off = p.orpb ? (size_t)(row / p.orpb) * p.obs + (size_t)(row % p.orpb) * p.ldc : (size_t)row * p.ldc;
-  if constexpr (GEGLU) {
-    constexpr int HALF = BN / 2;
-    constexpr int NCH = HALF / 32;
+  constexpr int WOUT = GEGLU ? BN / 2 : BN;           // output columns of the tile
+  constexpr int NCH = WOUT / 32;
+  const bool tma_res = !GEGLU && p.tma_res;
+  const bool has_res = !GEGLU && p.residual != nullptr;
+  const float* rb = (!GEGLU && p.rowbias && row_ok) ? p.rowbias + (size_t)(row / p.rows_per_batch) * p.ld_rowbias : nullptr;
 #pragma unroll 1
-    for (int c = half ? (NCH + 1) / 2 : 0; c < (half ? NCH : (NCH + 1) / 2); ++c) {
-      uint32_t rx[32], rg[32];
-      tmem_ld32(taddr + c * 32, rx);
-      tmem_ld32(taddr + HALF + c * 32, rg);
-      tmem_ld_wait();
-      float v[32];
-      const float* bx = p.bias + (size_t)n_blk * BN + c * 32;
-      const float* bg = bx + HALF;
-      if (p.ln_stats) {
-        const float* sx = p.ln_colsum + (size_t)n_blk * BN + c * 32;
-        const float* sg = sx + HALF;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 ux = __ldg(reinterpret_cast<const float4*>(sx + j));
-          const float4 ug = __ldg(reinterpret_cast<const float4*>(sg + j));
-          rx[j + 0] = __float_as_uint(ln_rstd * (__uint_as_float(rx[j + 0]) - ln_mu * ux.x));
-          rx[j + 1] = __float_as_uint(ln_rstd * (__uint_as_float(rx[j + 1]) - ln_mu * ux.y));
-          rx[j + 2] = __float_as_uint(ln_rstd * (__uint_as_float(rx[j + 2]) - ln_mu * ux.z));
-          rx[j + 3] = __float_as_uint(ln_rstd * (__uint_as_float(rx[j + 3]) - ln_mu * ux.w));
-          rg[j + 0] = __float_as_uint(ln_rstd * (__uint_as_float(rg[j + 0]) - ln_mu * ug.x));
-          rg[j + 1] = __float_as_uint(ln_rstd * (__uint_as_float(rg[j + 1]) - ln_mu * ug.y));
-          rg[j + 2] = __float_as_uint(ln_rstd * (__uint_as_float(rg[j + 2]) - ln_mu * ug.z));
-          rg[j + 3] = __float_as_uint(ln_rstd * (__uint_as_float(rg[j + 3]) - ln_mu * ug.w));
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 tx = __ldg(reinterpret_cast<const float4*>(bx + j));
-        const float4 tg = __ldg(reinterpret_cast<const float4*>(bg + j));
-        v[j + 0] = (__uint_as_float(rx[j + 0]) + tx.x) * gelu_erf_f(__uint_as_float(rg[j + 0]) + tg.x);
-        v[j + 1] = (__uint_as_float(rx[j + 1]) + tx.y) * gelu_erf_f(__uint_as_float(rg[j + 1]) + tg.y);
-        v[j + 2] = (__uint_as_float(rx[j + 2]) + tx.z) * gelu_erf_f(__uint_as_float(rg[j + 2]) + tg.z);
-        v[j + 3] = (__uint_as_float(rx[j + 3]) + tx.w) * gelu_erf_f(__uint_as_float(rg[j + 3]) + tg.w);
-      }
-      if (p.tma_out) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-        epi_tma_store(p, tmOut, ew, pk, lane, row0, n_blk * HALF + c * 32);
-      } else if (row_ok) {
-        epi_store_bf16(reinterpret_cast<bf16*>(p.out) + out_off + (size_t)n_blk * HALF + c * 32, v, p.wide != 0);
-      }
+  for (int c = grp; c < NCH; c += 4) {
+    const int ocol = n_blk * WOUT + c * 32;           // first output column of the chunk
+    if (tma_res) {                                    // requested at the tile prologue (first chunk) or one chunk ago
+      mbar_wait(ew.res_bar, ew.res_phase);
+      ew.res_phase ^= 1u;
     }
-  } else {
-    const float* rb = (p.rowbias && row_ok) ? p.rowbias + (size_t)(row / p.rows_per_batch) * p.ld_rowbias : nullptr;
-    constexpr int NCH = BN / 32;
-    const int c_begin = half ? (NCH + 1) / 2 : 0, c_end = half ? NCH : (NCH + 1) / 2;
-    const bool has_res = p.residual != nullptr && (row_ok || p.tma_res);
-    const bf16* res_row = (has_res && !p.tma_res) ? p.residual + (size_t)row * p.ldr + (size_t)n_blk * BN : nullptr;
-    uint32_t r_next[32];
-    if (c_begin < c_end) tmem_ld32(taddr + c_begin * 32, r_next);
-#pragma unroll 1
-    for (int c = c_begin; c < c_end; ++c) {
-      uint32_t r[32];
-      uint4 res_cur[4];
-      if (p.tma_res) {
-        // this chunk's residual was requested one chunk (or one tile prologue) ago; request the next one right away
-        const int buf = ew.res_buf ^ 1;               // the buffer issued last
-        epi_res_take(ew, buf, lane, res_cur);
-        if (c + 1 < c_end) epi_res_issue(tmRes, ew, lane, row0, n_blk * BN + (c + 1) * 32);
+    if (p.tma_out) {                                  // the staging buffer of this warp's previous chunk has been read out
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+    }
+    float st_sum = 0.f, st_sq = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float v[16];
+      if constexpr (GEGLU) {
+        constexpr int HALF = BN / 2;
+        uint32_t rx[16], rg[16];
+        tmem_ld16(taddr + c * 32 + h * 16, rx);
+        tmem_ld16(taddr + HALF + c * 32 + h * 16, rg);
+        tmem_ld_wait();
+        const int wcol = n_blk * BN + c * 32 + h * 16;          // packed weight row of the x half ([128 x | 128 gate] per tile)
+        float g[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(rx[j]); g[j] = __uint_as_float(rg[j]); }
+        if (p.ln_stats) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 ux = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + wcol + j));
+            const float4 ug = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + wcol + HALF + j));
+            v[j] = ln_rstd * (v[j] - ln_mu * ux.x); v[j + 1] = ln_rstd * (v[j + 1] - ln_mu * ux.y);
+            v[j + 2] = ln_rstd * (v[j + 2] - ln_mu * ux.z); v[j + 3] = ln_rstd * (v[j + 3] - ln_mu * ux.w);
+            g[j] = ln_rstd * (g[j] - ln_mu * ug.x); g[j + 1] = ln_rstd * (g[j + 1] - ln_mu * ug.y);
+            g[j + 2] = ln_rstd * (g[j + 2] - ln_mu * ug.z); g[j + 3] = ln_rstd * (g[j + 3] - ln_mu * ug.w);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 tx = __ldg(reinterpret_cast<const float4*>(p.bias + wcol + j));
+          const float4 tg = __ldg(reinterpret_cast<const float4*>(p.bias + wcol + HALF + j));
+          v[j] = (v[j] + tx.x) * gelu_erf_f(g[j] + tg.x); v[j + 1] = (v[j + 1] + tx.y) * gelu_erf_f(g[j + 1] + tg.y);
+          v[j + 2] = (v[j + 2] + tx.z) * gelu_erf_f(g[j + 2] + tg.z); v[j + 3] = (v[j + 3] + tx.w) * gelu_erf_f(g[j + 3] + tg.w);
+        }
       } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) res_cur[i] = res_pre[i];
-        if (has_res && c + 1 < c_end)             // next chunk's residual: in flight while this chunk is processed
-          load_res_chunk(res_row + (c + 1) * 32, res_pre, p.wide != 0);
-      }
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) r[j] = r_next[j];
-      if (c + 1 < c_end) tmem_ld32(taddr + (c + 1) * 32, r_next);      // next chunk's accumulators: in flight during the math
-      const int n0 = n_blk * BN + c * 32;
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      if (p.ln_stats) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + j));
-          v[j] = ln_rstd * (v[j] - ln_mu * t.x); v[j + 1] = ln_rstd * (v[j + 1] - ln_mu * t.y);
-          v[j + 2] = ln_rstd * (v[j + 2] - ln_mu * t.z); v[j + 3] = ln_rstd * (v[j + 3] - ln_mu * t.w);
+        uint32_t r[16];
+        tmem_ld16(taddr + c * 32 + h * 16, r);
+        uint4 res[2] = {};
+        if (has_res) {
+          if (tma_res) epi_res_half(ew, lane, h, res);
+          else if (row_ok) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + ocol + h * 16);
+            res[0] = __ldg(r4); res[1] = __ldg(r4 + 1);
+          }
         }
-      }
-      if (p.bias) {
+        tmem_ld_wait();
+        const int n0 = ocol + h * 16;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-          v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.ln_stats) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + j));
+            v[j] = ln_rstd * (v[j] - ln_mu * t.x); v[j + 1] = ln_rstd * (v[j + 1] - ln_mu * t.y);
+            v[j + 2] = ln_rstd * (v[j + 2] - ln_mu * t.z); v[j + 3] = ln_rstd * (v[j + 3] - ln_mu * t.w);
+          }
         }
-      }
-      if (rb) {
+        if (p.bias) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(rb + n0 + j));
-          v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+          for (int j = 0; j < 16; j += 4) add4(v, j, __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j)));
         }
-      }
-      if (p.act == GLG_ACT_SILU) {
+        if (rb) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-      }
-      if (p.gate) {
+          for (int j = 0; j < 16; j += 4) add4(v, j, __ldg(reinterpret_cast<const float4*>(rb + n0 + j)));
+        }
+        if (p.act == GLG_ACT_SILU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= gate;
-      }
-      if (row_ok || p.tma_out) {
+          for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+        }
+        if (p.gate) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= gate;
+        }
         if (has_res) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < 2; ++i) {
             float2 f;
-            f = unpack_bf16x2(res_cur[i].x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
-            f = unpack_bf16x2(res_cur[i].y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
-            f = unpack_bf16x2(res_cur[i].z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
-            f = unpack_bf16x2(res_cur[i].w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+            f = unpack_bf16x2(res[i].x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
+            f = unpack_bf16x2(res[i].y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
+            f = unpack_bf16x2(res[i].z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
+            f = unpack_bf16x2(res[i].w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
           }
         }
         if (p.out_fp32) {
-          float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + n0);
+          if (row_ok) {
+            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + n0);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        } else {
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-          if (p.stats_out && row_ok) {
-            // statistics of the values AS STORED (bf16-rounded): exactly what the consumer GEMM reads.  One partial
-            // per 32-column chunk, slot = global chunk index: independent of the tile shape, so the consumer's
-            // fixed-order sum is bit-identical whatever kernel variant produced the rows.  SLOT-major: the 32 lanes
-            // (consecutive rows) write 256 consecutive bytes.
-            float st_sum = 0.f, st_sq = 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float2 f = unpack_bf16x2(pk[j]);
-              st_sum += f.x + f.y;
-              st_sq = fmaf(f.x, f.x, fmaf(f.y, f.y, st_sq));
-            }
-            reinterpret_cast<float2*>(p.stats_out)[(size_t)(n0 >> 5) * p.stats_stride + row] = make_float2(st_sum, st_sq);
+            for (int i = 0; i < 4; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           }
-          if (p.tma_out) epi_tma_store(p, tmOut, ew, pk, lane, row0, n0);
-          else epi_store_packed(reinterpret_cast<bf16*>(p.out) + out_off + n0, pk, p.wide != 0);
+          continue;
         }
       }
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      if (!GEGLU && p.stats_out) {
+        // statistics of the values AS STORED (bf16-rounded): exactly what the consumer GEMM reads
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 f = unpack_bf16x2(pk[j]);
+          st_sum += f.x + f.y;
+          st_sq = fmaf(f.x, f.x, fmaf(f.y, f.y, st_sq));
+        }
+      }
+      if (p.tma_out) epi_stage_half(ew, lane, h, pk);
+      else if (row_ok) {
+        uint4* d4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + out_off + ocol + h * 16);
+        d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
     }
+    if (tma_res) {
+      __syncwarp();                                   // every lane holds its residual values: the buffer may be refilled
+      if (c + 4 < NCH) epi_res_issue(tmRes, ew, lane, row0, ocol + 128);
+    }
+    if (!GEGLU && p.stats_out && row_ok && !p.out_fp32) {
+      // one partial per 32-column chunk, slot = global chunk index: independent of the tile shape, so the consumer's
+      // fixed-order sum is bit-identical whatever kernel variant produced the rows.  SLOT-major: the 32 lanes
+      // (consecutive rows) write 256 consecutive bytes.
+      reinterpret_cast<float2*>(p.stats_out)[(size_t)(ocol >> 5) * p.stats_stride + row] = make_float2(st_sum, st_sq);
+    }
+    if (p.tma_out) epi_tma_store(p, tmOut, ew, lane, row0, ocol);
   }
 }
 
 // split-K: raw fp32 accumulators -> ws[split][row][n]
 template <int BN>
-__device__ __forceinline__ void epilogue_partial(const GemmKParams& p, uint32_t taddr, int row, int n_blk, int half, int split) {
+__device__ __forceinline__ void epilogue_partial(const GemmKParams& p, uint32_t taddr, int row, int n_blk, int grp, int split) {
   constexpr int NCH = BN / 32;
-  const int c_begin = half ? (NCH + 1) / 2 : 0, c_end = half ? NCH : (NCH + 1) / 2;
   float* dst = p.ws + ((size_t)split * p.M + row) * p.N + (size_t)n_blk * BN;
 #pragma unroll 1
-  for (int c = c_begin; c < c_end; ++c) {
-    uint32_t r[32];
-    tmem_ld32(taddr + c * 32, r);
-    tmem_ld_wait();
-    if (row < p.M) {
-      float4* o4 = reinterpret_cast<float4*>(dst + c * 32);
+  for (int c = grp; c < NCH; c += 4) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        o4[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+    for (int h = 0; h < 2; ++h) {
+      uint32_t r[16];
+      tmem_ld16(taddr + c * 32 + h * 16, r);
+      tmem_ld_wait();
+      if (row < p.M) {
+        float4* o4 = reinterpret_cast<float4*>(dst + c * 32 + h * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          o4[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+      }
     }
   }
 }
@@ -481,7 +470,7 @@ __global__ void splitk_reduce_kernel(const GemmKParams p) {
 }
 
 template <int BN, bool GEGLU, bool CTA2>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(640, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes, const GemmKParams p) {
   using Cfg = GemmCfg<BN, CTA2>;
@@ -501,7 +490,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAXST + ACC + a); };
   const uint32_t bfull_bar = bar_base + 8u * (2 * MAXST + 2 * ACC);
   const uint32_t tmem_slot = bar_base + 8u * (2 * MAXST + 2 * ACC + 1);
-  const uint32_t res_bars = bar_base + 8u * (2 * MAXST + 2 * ACC + 2);      // 8 epilogue warps x 2
+  const uint32_t res_bars = bar_base + 8u * (2 * MAXST + 2 * ACC + 2);      // 16 epilogue warps
 
   pdl_trigger();          // the next kernel may start its prologue while this one runs (it waits before touching memory)
   const int warp = threadIdx.x >> 5;
@@ -513,9 +502,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(bfull_bar, 1);
-    for (int i = 0; i < 16; ++i) mbar_init(res_bars + 8u * i, 1);
-    // accumulator drained: one arrive per epilogue warp, from both CTAs of a pair (on the leader's barrier)
-    for (int a = 0; a < ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), CTA2 ? 16 : 8); }
+    for (int i = 0; i < 16; ++i) mbar_init(res_bars + 8u * i, 1);          // one per epilogue warp
+    // accumulator drained: one arrive per epilogue warp (16), from both CTAs of a pair (on the leader's barrier)
+    for (int a = 0; a < ACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), CTA2 ? 32 : 16); }
     fence_barrier_init();
   }
   if (warp == 0) {
@@ -648,18 +637,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (++acc == ACC) { acc = 0; acc_phase ^= 1u; }
     }
-  } else if (warp >= 2) {
-    // ===================== epilogue (each CTA: its own 128 accumulator rows) =====================
+  } else if (warp >= 4) {
+    // ===================== epilogue (each CTA: its own 128 accumulator rows; 16 warps) =====================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;             // which half of the column chunks this warp handles
+    const int grp = (warp - 4) >> 2;              // column group: chunks grp, grp + 4, ...
     int acc = 0; uint32_t acc_phase = 0;
     const float gate = p.gate ? __ldg(p.gate) : 1.0f;
     const uint32_t tempty_leader0 = CTA2 ? mapa_cluster(tempty_bar(0), 0) : tempty_bar(0);   // consecutive stages: +8 bytes
     EpiWarp ew;
-    ew.out_stage = base + p.epi_off + (uint32_t)(warp - 2) * 4096u;
-    ew.res_stage = base + p.epi_off + 32768u + (uint32_t)(warp - 2) * 4096u;
-    ew.res_bar = res_bars + 16u * (uint32_t)(warp - 2);
-    ew.res_phase = 0; ew.out_buf = 0; ew.res_buf = 0;
+    ew.out_stage = base + p.epi_off + (uint32_t)(warp - 4) * 2048u;
+    ew.res_stage = base + p.epi_off + 32768u + (uint32_t)(warp - 4) * 2048u;
+    ew.res_bar = res_bars + 8u * (uint32_t)(warp - 4);
+    ew.res_phase = 0;
+    constexpr int NCH_OUT = (GEGLU ? BN / 2 : BN) / 32;
     int tile, split, m_blk, n_blk;
     for (int it = 0; get_work(it, tile, split, m_blk, n_blk); ++it) {
       const int row = m_blk * ROWS_PER_TILE + (int)rank * 128 + q * 32 + lane;
@@ -672,20 +662,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ln_mu = s1 * p.inv_k;
         ln_rstd = rsqrtf(fmaxf(s2 * p.inv_k - ln_mu * ln_mu, 0.f) + p.ln_eps);
       }
-      uint4 res_pre[4] = {};
-      if (!GEGLU && p.residual && p.splits == 1) {
-        constexpr int NCH = BN / 32;
-        const int c_begin = half ? (NCH + 1) / 2 : 0, c_end = half ? NCH : (NCH + 1) / 2;
-        if (c_begin < c_end) {
-          if (p.tma_res) epi_res_issue(&tmRes, ew, lane, row - lane, n_blk * BN + c_begin * 32);
-          else if (row < p.M) load_res_chunk(p.residual + (size_t)row * p.ldr + (size_t)n_blk * BN + c_begin * 32, res_pre, p.wide != 0);
-        }
-      }
+      if (!GEGLU && p.tma_res && p.splits == 1 && grp < NCH_OUT)
+        epi_res_issue(&tmRes, ew, lane, row - lane, n_blk * BN + grp * 32);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      if (p.splits > 1) epilogue_partial<BN>(p, taddr, row, n_blk, half, split);
-      else epilogue_tile<BN, GEGLU>(p, taddr, row, n_blk, half, gate, ln_mu, ln_rstd, res_pre, &tmOut, &tmRes, ew, lane);
+      if (p.splits > 1) epilogue_partial<BN>(p, taddr, row, n_blk, grp, split);
+      else epilogue_tile<BN, GEGLU>(p, taddr, row, n_blk, grp, gate, ln_mu, ln_rstd, &tmOut, &tmRes, ew, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -730,7 +713,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   } else {
     grid = tiles < num_sms() ? tiles : num_sms();
   }
-  cudaError_t e = launch_k(kern, dim3(grid), dim3(320), smem, st, CTA2 ? 2 : 1, ta, tb, tout, tres, p);
+  cudaError_t e = launch_k(kern, dim3(grid), dim3(640), smem, st, CTA2 ? 2 : 1, ta, tb, tout, tres, p);
   count_launch();
   if (e != cudaSuccess) return set_error(std::string("gemm launch: ") + cudaGetErrorString(e));
   if (check_launch("gemm launch")) return -1;
@@ -780,8 +763,10 @@ static void pick_tile(int M, int N, int num_kb, bool geglu, bool conv, int max_s
   float best = 1e30f; int best_bn = 0, best_pair = 0, best_s = 1, best_res = 0;
   for (int pair = 0; pair < 2; ++pair) {
     if (pair && (g_cta2_mode == 1 || M <= 128)) continue;
-    // measured on B200 (profiles/): pairing pays only for large, long-K, N % 256 == 0 problems; the 3x3 convs tie
-    if (pair && g_cta2_mode == 0 && (conv || N % 256 || num_kb < 16 || M < 4096)) continue;      // (sweep_bn: M = 2048 pairs lose 20 %)
+    // measured on B200 (profiles/): pairing pays for large, long-K, N % 256 == 0 GEMMs (M = 2048 pairs lose 20 %) and, by
+    // 3-10 %, for the 3x3 convolutions from 16x16 up at 2B = 8 (profiles/r2_kernels.txt); never for the split-K cases
+    if (pair && g_cta2_mode == 0 && !conv && (N % 256 || num_kb < 16 || M < 4096)) continue;
+    if (pair && g_cta2_mode == 0 && conv && M < 2048) continue;
     if (!pair && g_cta2_mode == 2 && M > 128) {
       bool any = false;
       for (int i = 0; i < 3; ++i) any |= (N % cands[i] == 0) && (!geglu || cands[i] == 256);
@@ -793,7 +778,7 @@ static void pick_tile(int M, int N, int num_kb, bool geglu, bool conv, int max_s
       if (geglu && bn != 256) continue;
       if (g_force_bn && bn != g_force_bn && (N % g_force_bn == 0) && !geglu) continue;
       if (pair && bn < 128) continue;                    // per-CTA half of B must stay a whole number of KiB
-      if (pair && g_cta2_mode == 0 && bn != 256) continue;
+      if (pair && g_cta2_mode == 0 && !conv && bn != 256) continue;
       const int rows = pair ? 256 : 128;
       const int tiles = ((M + rows - 1) / rows) * (N / bn);
       const int units = pair ? sms / 2 : sms;

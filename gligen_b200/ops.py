@@ -219,6 +219,13 @@ class CudaOps:
                                                B, N, F_, nc, freqs, self._stream()), "glg_position_features")
         self._note("position_features")
 
+    def softmax_rows(self, s, p, scale: float):
+        """s fp32 [rows, cols] (row stride free) -> p bf16 [rows, cols] = softmax(scale * s) along the last dim."""
+        assert s.dtype == torch.float32 and s.dim() == 2 and s.stride(1) == 1 and p.dim() == 2 and p.stride(1) == 1 and p.shape == s.shape
+        L.check(self.lib.glg_softmax_rows(s.data_ptr(), s.stride(0), p.data_ptr(), p.stride(0), s.shape[0], s.shape[1], float(scale), self._stream()),
+                "glg_softmax_rows")
+        self._note("softmax_rows", 0.0, 6.0 * s.numel())
+
     def cast(self, x, y):
         """fp32 -> activation dtype, contiguous."""
         assert x.is_contiguous() and y.is_contiguous() and x.dtype == torch.float32 and x.numel() == y.numel()

@@ -368,7 +368,11 @@ class VAEDecoderConfig:
 
 NAMED_VAE_CONFIGS = {
     "sd14_vae": VAEDecoderConfig(),
-    "tiny_vae": VAEDecoderConfig(name="tiny_vae", ch=32, ch_mult=(1, 2), num_res_blocks=1, latent_size=8),
+    "tiny_vae": VAEDecoderConfig(name="tiny_vae", ch=32, ch_mult=(1, 2), num_res_blocks=1, latent_size=8),      # oracle only (32 channels)
+    # channel counts that are multiples of 64 (tensor-core tiles): 8x8 -> 16x16, and a 64x64 -> 256x256 case whose last
+    # level is wider than one 128-pixel tile
+    "tiny_vae64": VAEDecoderConfig(name="tiny_vae64", ch=64, ch_mult=(1, 2), num_res_blocks=1, latent_size=8),
+    "small_vae": VAEDecoderConfig(name="small_vae", ch=64, ch_mult=(1, 1, 2), num_res_blocks=1, latent_size=64),
 }
 
 

@@ -141,7 +141,8 @@ int glg_layernorm(const void* x, int64_t x_batch, void* y, int64_t y_batch, cons
  * w fp32 packed [9][Cin][Cout] (tap-major), Cin = C0 + C1.  openaimodel.py:305,454. */
 int glg_conv_in(const float* x, int32_t C0, const float* extra, int32_t C1, const float* w, const float* bias,
                 void* out, int64_t ldo, int32_t B, int32_t H, int32_t Wd, int32_t Cout, void* stream);
-/* Last conv: NHWC bf16 (already GN+SiLU'd) -> NCHW fp32 eps.  w fp32 packed [9][Cout][Cin], Cout in {4, 8}.  openaimodel.py:391-395. */
+/* Last conv: NHWC bf16 (already GN+SiLU'd) -> NCHW fp32 eps.  w fp32 packed [9][Cout][Cin], Cout in {3, 4, 8}.  openaimodel.py:391-395;
+ * Cout = 3 is the VAE decoder's conv_out (model.py:529-533). */
 int glg_conv_out(const void* x, int64_t ldx, const float* w, const float* bias, float* out,
                  int32_t B, int32_t H, int32_t Wd, int32_t Cin, int32_t Cout, void* stream);
 /* nearest 2x upsample, NHWC bf16 (openaimodel.py:79 F.interpolate). */
@@ -160,6 +161,9 @@ int glg_timestep_embedding(const int64_t* t, void* out, int32_t B, int32_t dim, 
 int glg_position_features(const float* feat, int64_t feat_batch_stride, const float* feat_mask, const float* null_feat,
                           const float* coords, const float* pos_mask, const float* null_pos, void* out, int64_t ldo,
                           int32_t B, int32_t N, int32_t F, int32_t ncoord, int32_t freqs, void* stream);
+/* Row softmax: p[r, c] = softmax_c(scale * s[r, c]) as bf16 (fp32 scores in, rows normalised before rounding).  The VAE
+ * decoder's single-head attention over H*W tokens (model.py:178-202: torch.bmm + softmax + torch.bmm; head dim 512). */
+int glg_softmax_rows(const float* s, int64_t lds, void* p, int64_t ldp, int64_t rows, int32_t cols, float scale, void* stream);
 /* fp32 -> bf16 cast of a contiguous buffer (context / weights staging). */
 int glg_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
 

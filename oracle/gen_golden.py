@@ -314,6 +314,8 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     if args.vae:
         run_vae("tiny_vae", B=2)
+        run_vae("tiny_vae64", B=2)
+        run_vae("small_vae", B=1, store_half=True)
         run_vae("sd14_vae", B=1, store_half=True)
         sys.exit(0)
     if args.configs345:

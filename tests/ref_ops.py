@@ -86,6 +86,10 @@ class RefOps:
         o = torch.einsum("bhij,bhjc->bhic", sim.softmax(dim=-1), vf)
         out.copy_(o.permute(0, 2, 1, 3).reshape(B, Lq, heads * d_head).to(out.dtype))
 
+    def softmax_rows(self, s, p, scale):
+        self.launches += 1
+        p.copy_(torch.softmax(s.float() * scale, dim=-1).to(p.dtype))
+
     def groupnorm(self, x, y, gamma, beta, stats, groups, eps, silu):
         self.launches += 2
         h = F.group_norm(x.float().permute(0, 2, 1), groups, gamma, beta, eps)

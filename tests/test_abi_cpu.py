@@ -115,7 +115,8 @@ def test_host_schedule_and_adapters():
 def test_tile_picker_choices_are_valid():
     """Host-side tile picker (csrc/gemm_tc.cu pick_tile) over every GEMM / conv shape of the SD-1.4 forward at 2B = 8
     and at B = 1: the tile width divides N, GEGLU keeps the 256-wide interleaved tile, K is only split when allowed and
-    when each split keeps >= 16 K blocks, CTA pairs only for large plain GEMMs with N % 256 == 0."""
+    when each split keeps >= 16 K blocks, CTA pairs only for large plain GEMMs with N % 256 == 0 and for 3x3 convolutions
+    with M >= 2048."""
     import ctypes as C
     from gligen_b200 import lib as L
     lib = L.load()
@@ -136,10 +137,11 @@ def test_tile_picker_choices_are_valid():
                     assert not geglu or bn == 256
                     assert sp >= 1 and (can_split or sp == 1)
                     assert sp == 1 or (K // 64) // sp >= 16
-                    assert not pair or (M >= 4096 and N % 256 == 0 and bn == 256 and sp == 1)
+                    assert not (pair & 1) or (M >= 4096 and N % 256 == 0 and bn == 256 and sp == 1)
+                    assert not (pair >> 8), "weights-resident tiles are opt-in (GLG_GEMM_BRES)"
         for (H, Cin, Cout) in ((64, 320, 320), (64, 960, 320), (32, 640, 640), (32, 1920, 640), (16, 1280, 1280), (16, 2560, 1280), (8, 1280, 1280), (8, 2560, 1280)):
             bn, pair, sp = pick(rows * H * H, Cout, Cin, 0, 1, 1)
-            assert Cout % bn == 0 and not pair and sp >= 1
+            assert Cout % bn == 0 and sp >= 1 and (not (pair & 1) or (rows * H * H >= 2048 and sp == 1 and bn >= 128))
             assert sp == 1 or (9 * Cin // 64) // sp >= 16
     # the 8x8 level at 2B = 8 (M = 512) leaves most SMs idle without a K split
     assert pick(512, 1280, 2560, 0, 1, 1)[2] > 1

