@@ -175,21 +175,29 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(s_full(g), (uint32_t)(it & 1));
       tc_fence_after();
       const int valid = p.Lk - j * BN;           // < 64 only in the last tile: keys [valid, 64) are padding
-      // ---- pass 1: row maximum of this tile
+      // ---- pass 1: row maximum of this tile: all 64 scores with ONE TMEM round trip (the registers die right after)
       float mx = -INFINITY;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t sv[32];
-        tmem_ld32(s_addr + hh * 32, sv);
+      {
+        uint32_t lo[32], hi[32];
+        tmem_ld32(s_addr, lo);
+        tmem_ld32(s_addr + 32, hi);
         tmem_ld_wait();
         if (valid < BN) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (hh * 32 + i >= valid) sv[i] = 0xff800000u;
+          for (int i = 0; i < 32; ++i) {
+            if (i >= valid) lo[i] = 0xff800000u;
+            if (32 + i >= valid) hi[i] = 0xff800000u;
+          }
         }
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])));
+        for (int i = 0; i < 32; i += 2) {
+          mx = fmaxf(mx, fmaxf(__uint_as_float(lo[i]), __uint_as_float(lo[i + 1])));
+          mx = fmaxf(mx, fmaxf(__uint_as_float(hi[i]), __uint_as_float(hi[i + 1])));
+        }
       }
+      // pass 2 re-reads the scores in 16-column pieces, each requested one piece ahead of its use
+      uint32_t cur[16];
+      tmem_ld16(s_addr, cur);
       const float m_new = fmaxf(m_ref, mx);
       if (it == 0) {
         m_ref = m_new;
@@ -211,26 +219,31 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tmem_st_wait();
         }
       }
-      // ---- pass 2: P = exp2((S - m_ref) * scale) -> bf16, written over the first 32 columns of S (scores of both
-      //      halves are re-read from TMEM; columns [16 hh, 16 hh + 16) of P only cover scores already consumed)
+      // ---- pass 2: P = exp2((S - m_ref) * scale) -> bf16, written over the first 32 columns of S.  P piece k lands in
+      //      columns [8k, 8k+8), which only cover score pieces <= k - all already in registers when it is written
       const float ms = m_ref * sl2;
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t sv[32];
-        tmem_ld32(s_addr + hh * 32, sv);
+      for (int k = 0; k < 4; ++k) {
         tmem_ld_wait();
-        uint32_t pk[16];
+        uint32_t nxt[16];
+        if (k < 3) tmem_ld16(s_addr + (k + 1) * 16, nxt);
+        uint32_t pk[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float a0 = ex2_approx2(fmaf(__uint_as_float(sv[2 * i]), sl2, -ms));
-          float a1 = ex2_approx2(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -ms));
+        for (int i = 0; i < 8; ++i) {
+          float a0 = ex2_approx2(fmaf(__uint_as_float(cur[2 * i]), sl2, -ms));
+          float a1 = ex2_approx2(fmaf(__uint_as_float(cur[2 * i + 1]), sl2, -ms));
           if (valid < BN) {
-            if (hh * 32 + 2 * i >= valid) a0 = 0.f;
-            if (hh * 32 + 2 * i + 1 >= valid) a1 = 0.f;
+            if (k * 16 + 2 * i >= valid) a0 = 0.f;
+            if (k * 16 + 2 * i + 1 >= valid) a1 = 0.f;
           }
           pk[i] = pack_bf16x2(a0, a1);
         }
-        tmem_st16(s_addr + hh * 16, pk);
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                     ::"r"(s_addr + k * 8), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+        if (k < 3) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+        }
       }
       tmem_st_wait();
       tc_fence_before();

@@ -69,6 +69,8 @@ struct GemmKParams {
   unsigned epi_off;               // byte offset (from the tile base) of the epilogue staging area
   long long stats_stride;         // stats_out / ln_stats are SLOT-major: element (slot, row) at [slot * stride + row]
   long long ln_stride;
+  int dbg;                        // scripts/micro knock-outs (results are garbage, time is real): 1 no TMA loads, 2 no MMAs,
+                                  // 4 no epilogue work (barrier protocol only), 8 no output stores
 };
 
 template <int BN, bool CTA2> struct GemmCfg {
@@ -255,7 +257,7 @@ __device__ __forceinline__ void epi_tma_store(const GemmKParams& p, const CUtens
 __device__ __forceinline__ void add4(float (&v)[16], int j, const float4 t) { v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
 
 template <int BN, bool GEGLU>
-__device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t taddr, int row, int n_blk, int grp, float gate,
+__device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t taddr, int row, int n_blk, int c0, float gate,
                                               float ln_mu, float ln_rstd, const CUtensorMap* tmOut, const CUtensorMap* tmRes,
                                               EpiWarp& ew, int lane) {
   const bool row_ok = row < p.M;
@@ -267,7 +269,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
   const bool has_res = !GEGLU && p.residual != nullptr;
   const float* rb = (!GEGLU && p.rowbias && row_ok) ? p.rowbias + (size_t)(row / p.rows_per_batch) * p.ld_rowbias : nullptr;
 #pragma unroll 1
-  for (int c = grp; c < NCH; c += 4) {
+  for (int c = c0; c < NCH; c += 4) {
     const int ocol = n_blk * WOUT + c * 32;           // first output column of the chunk
     if (tma_res) {                                    // requested at the tile prologue (first chunk) or one chunk ago
       mbar_wait(ew.res_bar, ew.res_phase);
@@ -291,23 +293,22 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
         float g[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) { v[j] = __uint_as_float(rx[j]); g[j] = __uint_as_float(rg[j]); }
-        if (p.ln_stats) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 ux = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + wcol + j));
-            const float4 ug = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + wcol + HALF + j));
-            v[j] = ln_rstd * (v[j] - ln_mu * ux.x); v[j + 1] = ln_rstd * (v[j + 1] - ln_mu * ux.y);
-            v[j + 2] = ln_rstd * (v[j + 2] - ln_mu * ux.z); v[j + 3] = ln_rstd * (v[j + 3] - ln_mu * ux.w);
-            g[j] = ln_rstd * (g[j] - ln_mu * ug.x); g[j + 1] = ln_rstd * (g[j + 1] - ln_mu * ug.y);
-            g[j + 2] = ln_rstd * (g[j + 2] - ln_mu * ug.z); g[j + 3] = ln_rstd * (g[j + 3] - ln_mu * ug.w);
-          }
-        }
+        // LayerNorm fold + bias as two FMAs per accumulator: rstd * acc + (bias - rstd * mu * colsum)
+        const float c1 = -ln_rstd * ln_mu;              // ln_rstd = 1, ln_mu = 0 without a fold
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
-          const float4 tx = __ldg(reinterpret_cast<const float4*>(p.bias + wcol + j));
-          const float4 tg = __ldg(reinterpret_cast<const float4*>(p.bias + wcol + HALF + j));
-          v[j] = (v[j] + tx.x) * gelu_erf_f(g[j] + tg.x); v[j + 1] = (v[j + 1] + tx.y) * gelu_erf_f(g[j + 1] + tg.y);
-          v[j + 2] = (v[j + 2] + tx.z) * gelu_erf_f(g[j + 2] + tg.z); v[j + 3] = (v[j + 3] + tx.w) * gelu_erf_f(g[j + 3] + tg.w);
+          float4 tx = __ldg(reinterpret_cast<const float4*>(p.bias + wcol + j));
+          float4 tg = __ldg(reinterpret_cast<const float4*>(p.bias + wcol + HALF + j));
+          if (p.ln_stats) {
+            const float4 ux = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + wcol + j));
+            const float4 ug = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + wcol + HALF + j));
+            tx.x = fmaf(ux.x, c1, tx.x); tx.y = fmaf(ux.y, c1, tx.y); tx.z = fmaf(ux.z, c1, tx.z); tx.w = fmaf(ux.w, c1, tx.w);
+            tg.x = fmaf(ug.x, c1, tg.x); tg.y = fmaf(ug.y, c1, tg.y); tg.z = fmaf(ug.z, c1, tg.z); tg.w = fmaf(ug.w, c1, tg.w);
+          }
+          v[j] = geglu_f(fmaf(v[j], ln_rstd, tx.x), fmaf(g[j], ln_rstd, tg.x));
+          v[j + 1] = geglu_f(fmaf(v[j + 1], ln_rstd, tx.y), fmaf(g[j + 1], ln_rstd, tg.y));
+          v[j + 2] = geglu_f(fmaf(v[j + 2], ln_rstd, tx.z), fmaf(g[j + 2], ln_rstd, tg.z));
+          v[j + 3] = geglu_f(fmaf(v[j + 3], ln_rstd, tx.w), fmaf(g[j + 3], ln_rstd, tg.w));
         }
       } else {
         uint32_t r[16];
@@ -325,14 +326,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
         if (p.ln_stats) {
+          // LayerNorm fold + bias as two FMAs per element: rstd * acc + (bias - rstd * mu * colsum)
+          const float c1 = -ln_rstd * ln_mu;
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             const float4 t = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + n0 + j));
-            v[j] = ln_rstd * (v[j] - ln_mu * t.x); v[j + 1] = ln_rstd * (v[j + 1] - ln_mu * t.y);
-            v[j + 2] = ln_rstd * (v[j + 2] - ln_mu * t.z); v[j + 3] = ln_rstd * (v[j + 3] - ln_mu * t.w);
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+            v[j] = fmaf(v[j], ln_rstd, fmaf(t.x, c1, bb.x)); v[j + 1] = fmaf(v[j + 1], ln_rstd, fmaf(t.y, c1, bb.y));
+            v[j + 2] = fmaf(v[j + 2], ln_rstd, fmaf(t.z, c1, bb.z)); v[j + 3] = fmaf(v[j + 3], ln_rstd, fmaf(t.w, c1, bb.w));
           }
-        }
-        if (p.bias) {
+        } else if (p.bias) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) add4(v, j, __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j)));
         }
@@ -396,17 +400,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
       // (consecutive rows) write 256 consecutive bytes.
       reinterpret_cast<float2*>(p.stats_out)[(size_t)(ocol >> 5) * p.stats_stride + row] = make_float2(st_sum, st_sq);
     }
-    if (p.tma_out) epi_tma_store(p, tmOut, ew, lane, row0, ocol);
+    if (p.tma_out && !(p.dbg & 8)) epi_tma_store(p, tmOut, ew, lane, row0, ocol);
   }
 }
 
 // split-K: raw fp32 accumulators -> ws[split][row][n]
 template <int BN>
-__device__ __forceinline__ void epilogue_partial(const GemmKParams& p, uint32_t taddr, int row, int n_blk, int grp, int split) {
+__device__ __forceinline__ void epilogue_partial(const GemmKParams& p, uint32_t taddr, int row, int n_blk, int c0, int split) {
   constexpr int NCH = BN / 32;
   float* dst = p.ws + ((size_t)split * p.M + row) * p.N + (size_t)n_blk * BN;
 #pragma unroll 1
-  for (int c = grp; c < NCH; c += 4) {
+  for (int c = c0; c < NCH; c += 4) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       uint32_t r[16];
@@ -574,7 +578,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(empty_bar(stage), phase ^ 1u);
         const uint32_t a_dst = base + stage * stage_bytes;
         const uint32_t b_dst = a_dst + Cfg::A_BYTES;
-        if (leader) {
+        if (leader && (p.dbg & 1)) {
+          if (!CTA2 || rank == 0) mbar_arrive(full_bar(stage));
+        } else if (leader) {
         // the leader CTA's barrier collects the bytes of both CTAs
         if (bres) mbar_arrive_expect_tx(full_bar(stage), Cfg::A_BYTES);
         else if (!CTA2) mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
@@ -623,6 +629,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint64_t adesc = umma_desc_kmajor_sw128(a_addr);
         const uint64_t bdesc = umma_desc_kmajor_sw128(bres ? bres_base + (uint32_t)kb * Cfg::B_BYTES : a_addr + Cfg::A_BYTES);
         if (leader) {
+          if (!(p.dbg & 2))
 #pragma unroll
           for (int k = 0; k < 4; ++k) {   // 4 x K=16 inside one 64-wide (128 B) swizzle atom: +32 B per step
             if constexpr (CTA2) umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
@@ -662,13 +669,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ln_mu = s1 * p.inv_k;
         ln_rstd = rsqrtf(fmaxf(s2 * p.inv_k - ln_mu * ln_mu, 0.f) + p.ln_eps);
       }
-      if (!GEGLU && p.tma_res && p.splits == 1 && grp < NCH_OUT)
-        epi_res_issue(&tmRes, ew, lane, row - lane, n_blk * BN + grp * 32);
+      // chunk -> column group rotates with the tile counter: with 5 chunks per tile (BN = 160) group 0 would otherwise
+      // own two chunks of EVERY tile and set the pace; over four tiles every group now handles five
+      const int c0 = (grp - it) & 3;
+      if (!GEGLU && p.tma_res && p.splits == 1 && !(p.dbg & 4) && c0 < NCH_OUT)
+        epi_res_issue(&tmRes, ew, lane, row - lane, n_blk * BN + c0 * 32);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-      if (p.splits > 1) epilogue_partial<BN>(p, taddr, row, n_blk, grp, split);
-      else epilogue_tile<BN, GEGLU>(p, taddr, row, n_blk, grp, gate, ln_mu, ln_rstd, &tmOut, &tmRes, ew, lane);
+      if (p.dbg & 4) {
+      } else if (p.splits > 1) epilogue_partial<BN>(p, taddr, row, n_blk, c0, split);
+      else epilogue_tile<BN, GEGLU>(p, taddr, row, n_blk, c0, gate, ln_mu, ln_rstd, &tmOut, &tmRes, ew, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -732,6 +743,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
 int g_force_bn = 0;     // test hooks (glg_debug_force_bn / glg_debug_gemm_cta2 / glg_debug_splitk)
 int g_splitk_mode = 0;  // 0 = heuristic, 1 = never, 2 = split whenever legal
 int g_cta2_mode = -1;   // 0 = heuristic, 1 = never pair, 2 = pair whenever legal; -1 = read GLG_GEMM_CTA2 (default 0)
+int g_gemm_dbg = 0;     // scripts/micro knock-out flags (GemmKParams::dbg)
 int g_epi_mode = -1;    // test hook: -1 = GLG_GEMM_EPI / default, 0 = per-thread epilogue accesses, 1 = TMA epilogue
 int g_bres_mode = -1;   // B-resident tiles: 0 = heuristic, 1 = never, 2 = whenever legal; -1 = read GLG_GEMM_BRES (default 0)
 
@@ -829,6 +841,7 @@ extern "C" void glg_debug_pick_tile(int M, int N, int K, int geglu, int conv, in
 }
 extern "C" void glg_debug_gemm_bres(int mode) { glg::g_bres_mode = mode; }
 extern "C" void glg_debug_gemm_epi(int mode) { glg::g_epi_mode = mode; }
+extern "C" void glg_debug_gemm_knockout(int flags) { glg::g_gemm_dbg = flags; }
 extern "C" void glg_debug_gemm_cta2(int mode) { glg::g_cta2_mode = mode; }
 extern "C" void glg_debug_splitk(int mode) { glg::g_splitk_mode = mode; }
 
@@ -880,6 +893,7 @@ extern "C" int glg_gemm(const GlgGemmArgs* a, void* stream) {
   p.splits = splits;
   p.ws = splits > 1 ? reinterpret_cast<float*>(a->splitk_ws) : nullptr;
   p.b_res = bres;
+  p.dbg = g_gemm_dbg;
   // ---- epilogue data path: TMA stores of the bf16 output, TMA loads of the residual (see the kernel comment)
   static int epi_mode = -1;       // GLG_GEMM_EPI: 0 = per-thread global accesses (the old path), 1 = TMA (default)
   if (epi_mode < 0) { const char* e = getenv("GLG_GEMM_EPI"); epi_mode = e ? atoi(e) : 1; }

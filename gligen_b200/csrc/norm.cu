@@ -36,11 +36,13 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
 // grid (chunks, B), every CTA co-resident (the launcher sizes the grid by the occupancy of this kernel);
 // blockDim = (C/8) * rpi, thread -> (fixed channel vector cv of 8 channels, row lane rl); a CTA owns rows
 // [chunk * rows_per_chunk, ...) of one sample.
-//   1. pivot: p_g = mean of row 0 of the sample over the group's channels (every CTA of a sample computes the same
-//      value in the same order).  All moments are accumulated on SHIFTED data d = x - p_g, so the variance
-//      S2/n - (S1/n)^2 never subtracts two large numbers (the raw E[x^2] - E[x]^2 form loses everything when
-//      |mean| >> std; util.py:223-225 runs F.group_norm in fp32, which is a two-pass / Welford computation).
-//   2. per-CTA partial (S1, S2) per group -> scratch; sample-wide barrier (arrive counter + spin; the counters reset
+//   1. SHIFTED moments: every channel is accumulated relative to its own pivot p_c = x[b, row 0, c] (one 16-byte load
+//      per thread, no reduction), so neither sum ever holds a large mean; when the channels of a group are merged the
+//      sums are moved onto the group's common pivot P_g = p_(first channel of g) by exact algebra
+//          S1' = S1 + n d,   S2' = S2 + 2 d S1 + n d^2,   d = p_c - P_g.
+//      The variance S2'/N - (S1'/N)^2 then cancels at most by the group's own between-channel spread - the raw
+//      E[x^2] - E[x]^2 form loses everything when |mean| >> std (util.py:223-225 runs F.group_norm in fp32: two-pass).
+//   2. per-CTA partial (S1', S2') per group -> scratch; sample-wide barrier (arrive counter + spin; the counters reset
 //      themselves when the last CTA leaves); every CTA then sums the partials of its sample in chunk order: no
 //      floating-point atomics anywhere, a forward is bit-reproducible run to run.
 //   3. apply: the activation is read a second time (an L2 hit: producer -> GroupNorm -> consumer tensors of this
@@ -54,15 +56,15 @@ __global__ void gn_fused_kernel(const bf16* __restrict__ x, long long ldx, bf16*
                                 int B, int HW, int C, int groups, float eps, int silu, int rows_per_chunk) {
   pdl_trigger();
   pdl_wait();
-  extern __shared__ float gn_sm[];          // [2][max(C, 512)] | pivot[groups] | mean[groups] | rstd[groups]
-  const int cmax = C > 512 ? C : 512;
-  float* s_sum = gn_sm;
-  float* s_sq = gn_sm + cmax;
-  float* s_piv = gn_sm + 2 * cmax;
-  float* s_mean = s_piv + groups;
-  float* s_rstd = s_mean + groups;
+  extern __shared__ float gn_sm[];          // [2][rpi][C] row-lane partials (>= 2 * 512 floats) | [C] pivots | mean[groups] | rstd[groups]
   const int vec = C >> 3;
   const int rpi = blockDim.x / vec;
+  const int red = rpi * C > 512 ? rpi * C : 512;
+  float* s_sum = gn_sm;
+  float* s_sq = gn_sm + red;
+  float* s_piv = gn_sm + 2 * red;
+  float* s_mean = s_piv + C;
+  float* s_rstd = s_mean + groups;
   const int cv = threadIdx.x % vec, rl = threadIdx.x / vec;
   const int b = blockIdx.y, chunks = gridDim.x;
   const int cpg = C / groups;
@@ -71,26 +73,13 @@ __global__ void gn_fused_kernel(const bf16* __restrict__ x, long long ldx, bf16*
   float* part_b = scratch + 128 + (long long)b * chunks * groups * 2;
   const bf16* xb = x + (long long)b * HW * ldx + cv * 8;
 
-  // ---- 1. pivots from row 0
-  if (rl == 0) {
-    float v[8];
-    load8(xb, v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s_sum[cv * 8 + j] = v[j];
-  }
-  __syncthreads();
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    float s = 0.f;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) s += s_sum[c];
-    s_piv[g] = s / (float)cpg;
-  }
-  __syncthreads();
+  // ---- 1. shifted moments of this CTA's rows (pivot = the channel's value in row 0 of the sample)
   float pv[8];
+  load8(xb, pv);
+  if (rl == 0) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) pv[j] = s_piv[(cv * 8 + j) / cpg];
-  __syncthreads();                           // s_sum is reused below
-
-  // ---- 2. shifted moments of this CTA's rows
+    for (int j = 0; j < 8; ++j) s_piv[cv * 8 + j] = pv[j];
+  }
   const int r0 = blockIdx.x * rows_per_chunk;
   const int r1 = min(HW, r0 + rows_per_chunk);
   float a[8], q[8];
@@ -115,20 +104,21 @@ __global__ void gn_fused_kernel(const bf16* __restrict__ x, long long ldx, bf16*
 #pragma unroll
     for (int j = 0; j < 8; ++j) { const float d = v[j] - pv[j]; a[j] += d; q[j] = fmaf(d, d, q[j]); }
   }
-  // fixed-order reduction over the rpi row lanes: lane rl == k adds in turn
-  for (int k = 0; k < rpi; ++k) {
-    if (rl == k) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (k == 0) { s_sum[cv * 8 + j] = a[j]; s_sq[cv * 8 + j] = q[j]; }
-        else { s_sum[cv * 8 + j] += a[j]; s_sq[cv * 8 + j] += q[j]; }
-      }
-    }
-    __syncthreads();
-  }
+  for (int j = 0; j < 8; ++j) { s_sum[rl * C + cv * 8 + j] = a[j]; s_sq[rl * C + cv * 8 + j] = q[j]; }
+  __syncthreads();
+  // one thread per group: its channels' row-lane partials in fixed order, moved onto the group's common pivot
+  const int rows_here = max(r1 - r0, 0);
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    const float P = s_piv[g * cpg];
     float s = 0.f, ss = 0.f;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { s += s_sum[c]; ss += s_sq[c]; }
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      float s1 = 0.f, s2 = 0.f;
+      for (int k = 0; k < rpi; ++k) { s1 += s_sum[k * C + c]; s2 += s_sq[k * C + c]; }
+      const float d = s_piv[c] - P;
+      s += fmaf((float)rows_here, d, s1);
+      ss += fmaf(d, fmaf((float)rows_here, d, 2.f * s1), s2);
+    }
     *reinterpret_cast<float2*>(part_b + ((long long)blockIdx.x * groups + g) * 2) = make_float2(s, ss);
   }
   // ---- sample-wide barrier: every CTA of sample b has published its partials
@@ -141,7 +131,7 @@ __global__ void gn_fused_kernel(const bf16* __restrict__ x, long long ldx, bf16*
     while (true) {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrive) : "memory");
       if (seen >= (unsigned)chunks) break;
-      __nanosleep(64);
+      __nanosleep(32);
       if (t0 == 0) t0 = globaltimer_ns();
       else if (globaltimer_ns() - t0 > 4000000000ull) {   // co-residency violated: trap instead of hanging the box
         printf("glg: groupnorm barrier timeout (sample %d chunk %d: %u of %d arrived)\n", b, blockIdx.x, seen, chunks);
@@ -170,7 +160,7 @@ __global__ void gn_fused_kernel(const bf16* __restrict__ x, long long ldx, bf16*
       const float inv_n = 1.f / ((float)HW * (float)cpg);
       const float m1 = ts * inv_n;                                       // mean of the shifted data
       const float var = fmaxf(tss * inv_n - m1 * m1, 0.f);
-      s_mean[threadIdx.x] = s_piv[threadIdx.x] + m1;
+      s_mean[threadIdx.x] = s_piv[threadIdx.x * cpg] + m1;
       s_rstd[threadIdx.x] = rsqrtf(var + eps);
     }
     if (threadIdx.x == 0) {
@@ -338,7 +328,9 @@ extern "C" int glg_groupnorm(const void* x, int64_t ldx, void* y, int64_t ldy, c
   if (C % 8 || C % groups || (ldx % 8) || (ldy % 8)) return set_error("glg_groupnorm: C and leading dims must be multiples of 8, C % groups == 0");
   if (C > 4096) return set_error("glg_groupnorm: C too large");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (HW <= 256 && ((C / groups) % 2 == 0)) {
+  static int small_mode = -1;        // GLG_GN_SMALL=0: the barrier kernel also for H*W <= 256 (measured slower there: 19 vs 15 us)
+  if (small_mode < 0) { const char* e = getenv("GLG_GN_SMALL"); small_mode = e ? atoi(e) : 1; }
+  if (small_mode && HW <= 256 && ((C / groups) % 2 == 0)) {
     dim3 grid(groups, B);
     launch_k(gn_small_kernel, dim3(grid), dim3(256), 0, st, 1, (const bf16*)x, ldx, (bf16*)y, ldy, gamma, beta, HW, C, groups, eps, silu);
     count_launch();
@@ -349,17 +341,22 @@ extern "C" int glg_groupnorm(const void* x, int64_t ldx, void* y, int64_t ldy, c
   const int threads = vec * rpi;          // <= 512 for C <= 4096
   if (threads > 1024) return set_error("glg_groupnorm: C too large for one block");
   if (B > 64) return set_error("glg_groupnorm: at most 64 samples per call");
-  const size_t smem = (2 * (size_t)(C > 512 ? C : 512) + 3 * (size_t)groups) * sizeof(float);
+  const size_t red = (size_t)rpi * C > 512 ? (size_t)rpi * C : 512;
+  const size_t smem = (2 * red + (size_t)C + 2 * (size_t)groups) * sizeof(float);
   // every CTA of the grid must be resident at once (sample-wide barrier inside the kernel)
-  static int occ_cache[5] = {0, 0, 0, 0, 0};            // by block size class: occupancy of gn_fused_kernel
-  const int cls = threads <= 160 ? 0 : threads <= 256 ? 1 : threads <= 320 ? 2 : threads <= 512 ? 3 : 4;
-  if (!occ_cache[cls]) {
-    int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_fused_kernel, threads, 2 * 4096 * sizeof(float) + 3 * 64 * sizeof(float));
-    if (e != cudaSuccess || occ < 1) return set_error(std::string("glg_groupnorm: occupancy query failed: ") + cudaGetErrorString(e));
-    occ_cache[cls] = occ > 8 ? 8 : occ;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(gn_fused): ") + cudaGetErrorString(e));
+    attr_set = true;
   }
-  const int capacity = num_sms() * occ_cache[cls];
+  int occ = 0;
+  {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_fused_kernel, threads, smem);
+    if (e != cudaSuccess || occ < 1) return set_error(std::string("glg_groupnorm: occupancy query failed: ") + cudaGetErrorString(e));
+    if (occ > 8) occ = 8;
+  }
+  const int capacity = num_sms() * occ;
   int chunks = capacity / B;
   const int max_chunks = (HW + rpi * 4 - 1) / (rpi * 4);
   if (chunks > max_chunks) chunks = max_chunks;

@@ -25,15 +25,22 @@ def rnd(*shape, dtype=torch.bfloat16, scale=1.0):
 
 
 def timeit(name, fn, flops=0.0, nbytes=0.0, iters=20):
+    """GPU time per call: `iters` calls captured into ONE CUDA graph and replayed - the python / ctypes issue time of a
+    call (6-13 us, more than many of these kernels take) would otherwise be what a back-to-back loop measures."""
     if flt and flt not in name:
         return
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
-        fn()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
@@ -65,7 +72,7 @@ for (d, T, G, heads) in ((40, 4096, 30, 8), (80, 1024, 30, 8), (160, 256, 30, 8)
     ops.lib.glg_debug_attn_mode(0)
 
 # ---------------- GEMMs (token GEMMs of the transformer blocks) ----------------
-for cta2, bres, epi, cname in ((1, 1, 0, "stream-oldepi"), (1, 1, 1, "stream"), (1, 2, 1, "resident"), (2, 1, 1, "2cta"), (0, 0, 1, "auto")):
+for cta2, bres, epi, cname in ((1, 1, 0, "stream-oldepi"), (1, 1, 1, "stream"), (1, 2, 1, "resident"), (2, 1, 1, "2cta"), (0, -1, -1, "auto")):
   ops.lib.glg_debug_gemm_cta2(cta2)
   ops.lib.glg_debug_gemm_bres(bres)
   ops.lib.glg_debug_gemm_epi(epi)
