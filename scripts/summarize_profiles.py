@@ -59,6 +59,42 @@ def launches(tag):
     print("wrote launch list summary:", len(rows), "launches")
 
 
+def traffic(tag):
+    """profiles/<tag>_gemm_dram_traffic.json from gpurun_out/traffic_<tag>.csv (ncu --metrics dram__bytes_read.sum,
+    dram__bytes_write.sum -k regex:gemm_tc over bench.py --plms-steps 1); read by bench.py for roofline.traffic."""
+    path = os.path.join(OUT, f"traffic_{tag}.csv")
+    if not os.path.exists(path):
+        return
+    with open(path) as f:
+        lines = [l for l in f if not l.startswith("==")]
+    rd = csv.DictReader(io.StringIO("".join(lines)))
+    rdb, wrb, ids = 0.0, 0.0, set()
+    for r in rd:
+        name = r.get("Metric Name", "")
+        if not name.startswith("dram__bytes"):
+            continue
+        v = float(r["Metric Value"].replace(",", ""))
+        unit = r.get("Metric Unit", "byte").lower()
+        scale = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+        ids.add(r["ID"])
+        if "read" in name:
+            rdb += v * scale
+        else:
+            wrb += v * scale
+    n = max(len(ids), 1)
+    alg = None
+    bpo = os.path.join(OUT, "bench_per_op.json")
+    if os.path.exists(bpo):
+        ops = [o for o in json.load(open(bpo)) if o["kind"] in ("gemm", "conv3x3")]
+        alg = sum(o["mbytes"] for o in ops) * 1e6 / max(len(ops), 1)
+    out = {"kernel": "gemm_tc_kernel", "launches": n, "dram_bytes_read_per_launch": rdb / n, "dram_bytes_write_per_launch": wrb / n,
+           "algorithmic_bytes_per_launch": alg,
+           "how": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:gemm_tc_kernel over bench.py --steps 1 "
+                  "--warmup 1 --plms-steps 1 (B200; every launch serialised and replayed, caches flushed between replays)"}
+    json.dump(out, open(os.path.join(PROF, f"{tag}_gemm_dram_traffic.json"), "w"), indent=1)
+    print("wrote traffic:", out)
+
+
 def full(tag, which):
     rep = os.path.join(OUT, f"prof_{which}_{tag}.ncu-rep")
     if not os.path.exists(rep):
@@ -85,5 +121,6 @@ def full(tag, which):
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     launches(tag)
+    traffic(tag)
     full(tag, "gemm")
     full(tag, "attn")
