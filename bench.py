@@ -67,8 +67,11 @@ def parse(argv=None):
     args = ap.parse_args(argv)
     if args.preset:
         pr = PRESETS[args.preset]
-        args.config, args.alpha_type = pr["config"], pr["alpha_type"]
-        if "--batch" not in (argv or sys.argv):
+        given = argv if argv is not None else sys.argv
+        args.config = pr["config"]
+        if "--alpha-type" not in given:
+            args.alpha_type = pr["alpha_type"]
+        if "--batch" not in given:
             args.batch = pr["batch"]
     return args
 
@@ -408,6 +411,9 @@ def run_ours(args, world, rank, local_rank, dev, quiet_extras=False):
         return ms
 
     eng = model.engine()
+    import contextlib
+    _quiet = contextlib.redirect_stdout(sys.stderr)       # "First conv layer is not restorable ..." (inpaint) belongs on stderr here
+    _quiet.__enter__()
     for _ in range(args.warmup):
         one_image_batch(False)
     clocks = ClockSampler(local_rank)
@@ -418,6 +424,7 @@ def run_ours(args, world, rank, local_rank, dev, quiet_extras=False):
     clk = clocks.stop()
     one_image_batch(True)
     ms_e2e = timed(args.steps, True)
+    _quiet.__exit__(None, None, None)
 
     total_images = (args.global_batch if strong else world * B) * args.steps
     value = total_images / (ms / 1e3)
@@ -439,7 +446,7 @@ def run_ours(args, world, rank, local_rank, dev, quiet_extras=False):
             set_alpha_scale(model, 1.0 if atype[0] > 0 else 0.0)
             model._sync_scales(eng)
             N = resident_batch["points"].shape[1] if cfg.tokenizer == "keypoint" else resident_batch["boxes"].shape[1]
-            agg, per_op = kernel_pass(model, N, resident["uc"].shape[1], B)
+            agg, per_op = kernel_pass(model, N, resident["uc"].shape[1], min(B, eng.MAX_ROWS // 2))       # one chunk's plan
             tot_ms = sum(a[2] for a in agg.values())
             tc = [agg.get(k, [0, 0, 0, 0]) for k in ("gemm", "conv3x3")]
             tc_fl, tc_ms, tc_n = tc[0][0] + tc[1][0], tc[0][2] + tc[1][2], tc[0][3] + tc[1][3]

@@ -51,7 +51,20 @@ __device__ __forceinline__ float ex2_approx2(float x) {
   return y;
 }
 
-template <int DPAD>      // head dim rounded up to a multiple of 16 with one spare column for the row sums: d_head < DPAD <= 64
+// exp2 on the FMA / ALU pipes (Cody-Waite split + degree-3 polynomial on [-0.5, 0.5]; relative error 1e-4, far below the
+// bf16 rounding of P): a share of the exponentials is taken off the MUFU pipe, which bounds this kernel (16 exp2 / clk / SM).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;                 // 1.5 * 2^23: round(x) lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(0.05550411f, f, 0.24022651f);
+  p = fmaf(p, f, 0.69314718f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// POLY: of every 8 score pairs, the last POLY pairs take their exp2 from ex2_poly instead of the MUFU
+template <int DPAD, int POLY = 0>      // head dim rounded up to a multiple of 16 with one spare column for the row sums: d_head < DPAD <= 64
 __global__ void __launch_bounds__(320, 2)
 attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnTc2Params p) {
@@ -230,8 +243,9 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         uint32_t pk[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float a0 = ex2_approx2(fmaf(__uint_as_float(cur[2 * i]), sl2, -ms));
-          float a1 = ex2_approx2(fmaf(__uint_as_float(cur[2 * i + 1]), sl2, -ms));
+          const float x0 = fmaf(__uint_as_float(cur[2 * i]), sl2, -ms), x1 = fmaf(__uint_as_float(cur[2 * i + 1]), sl2, -ms);
+          float a0 = (i >= 8 - POLY) ? ex2_poly(x0) : ex2_approx2(x0);
+          float a1 = (i >= 8 - POLY) ? ex2_poly(x1) : ex2_approx2(x1);
           if (valid < BN) {
             if (k * 16 + 2 * i >= valid) a0 = 0.f;
             if (k * 16 + 2 * i + 1 >= valid) a1 = 0.f;
@@ -308,10 +322,12 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-template <int DPAD>
+int g_attn_tc2_poly = -1;      // -1: GLG_ATTN_POLY env (default 0); pairs of 8 whose exp2 runs on the FMA pipe (0, 1, 2, 3)
+
+template <int DPAD, int POLY>
 static int launch_attn_tc2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTc2Params& p, int B, cudaStream_t st) {
   static bool attr_set = false;
-  auto kern = attn_tc2_kernel<DPAD>;
+  auto kern = attn_tc2_kernel<DPAD, POLY>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, atc2::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(attn_tc2): ") + cudaGetErrorString(e));
@@ -349,13 +365,22 @@ int attention_tc2(const GlgAttnArgs* a, cudaStream_t st) {
   p.o = (bf16*)a->out; p.o_row = a->o_row; p.o_batch = a->o_batch;
   p.heads = a->heads; p.d = a->d_head; p.Lq = a->Lq; p.Lk = a->Lk;
   p.scale_log2 = a->scale * 1.4426950408889634f;
+  if (g_attn_tc2_poly < 0) { const char* e = getenv("GLG_ATTN_POLY"); g_attn_tc2_poly = e ? atoi(e) : 0; }
   switch (dpad) {
-    case 16: return launch_attn_tc2<16>(tq, tk, tv, p, a->B, st);
-    case 32: return launch_attn_tc2<32>(tq, tk, tv, p, a->B, st);
-    case 48: return launch_attn_tc2<48>(tq, tk, tv, p, a->B, st);
-    case 64: return launch_attn_tc2<64>(tq, tk, tv, p, a->B, st);
+    case 16: return launch_attn_tc2<16, 0>(tq, tk, tv, p, a->B, st);
+    case 32: return launch_attn_tc2<32, 0>(tq, tk, tv, p, a->B, st);
+    case 48:
+      switch (g_attn_tc2_poly) {
+        case 1: return launch_attn_tc2<48, 1>(tq, tk, tv, p, a->B, st);
+        case 2: return launch_attn_tc2<48, 2>(tq, tk, tv, p, a->B, st);
+        case 3: return launch_attn_tc2<48, 3>(tq, tk, tv, p, a->B, st);
+        default: return launch_attn_tc2<48, 0>(tq, tk, tv, p, a->B, st);
+      }
+    case 64: return launch_attn_tc2<64, 0>(tq, tk, tv, p, a->B, st);
   }
   return 1;
 }
 
 }  // namespace glg
+
+extern "C" void glg_debug_attn_poly_share(int pairs_of_8) { glg::g_attn_tc2_poly = pairs_of_8; }

