@@ -264,6 +264,72 @@ __global__ void gn_small_kernel(const bf16* __restrict__ x, long long ldx, bf16*
   }
 }
 
+// ---- small tensors, register-resident: one CTA per (group, sample) holds its whole [HW x cpg] slab in registers -----
+// (8-byte units; H*W * cpg <= 256 threads * MAXU units * 4): ONE global read, shifted moments, ONE write.  The 16x16 and 8x8
+// levels (C = 1280 / 1920 / 2560: cpg = 40 / 60 / 80) run 34 of the 61 norms of a UNet pass through this kernel.
+template <int MAXU>
+__global__ void __launch_bounds__(256) gn_reg_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     int HW, int C, int groups, float eps, int silu) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float red[2][8];
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int cpg = C / groups, upr = cpg >> 2;              // 8-byte units per row
+  const int total = HW * upr;
+  const bf16* xb = x + (long long)b * HW * ldx + g * cpg;
+  bf16* yb = y + (long long)b * HW * ldy + g * cpg;
+  uint2 u[MAXU];
+#pragma unroll
+  for (int i = 0; i < MAXU; ++i) {
+    const int idx = threadIdx.x + i * 256;
+    if (idx < total) {
+      const int r = idx / upr, c4 = idx - r * upr;
+      u[i] = __ldg(reinterpret_cast<const uint2*>(xb + (long long)r * ldx + c4 * 4));
+    } else {
+      u[i] = make_uint2(0u, 0u);
+    }
+  }
+  // pivot: element (row 0, first channel of the group); every thread reads it (L1 broadcast)
+  const float pivot = __bfloat162float(xb[0]);
+  float s = 0.f, ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXU; ++i) {
+    if (threadIdx.x + i * 256 < total) {
+      const float2 f0 = unpack_bf16x2(u[i].x), f1 = unpack_bf16x2(u[i].y);
+      const float d0 = f0.x - pivot, d1 = f0.y - pivot, d2 = f1.x - pivot, d3 = f1.y - pivot;
+      s += (d0 + d1) + (d2 + d3);
+      ss = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, ss))));
+    }
+  }
+  s = warp_sum(s); ss = warp_sum(ss);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = s; red[1][warp] = ss; }
+  __syncthreads();
+  float ts = 0.f, tss = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { ts += red[0][w]; tss += red[1][w]; }      // fixed order: deterministic
+  const float inv_n = 1.f / (float)(HW * cpg);
+  const float m1 = ts * inv_n;
+  const float mean = pivot + m1;
+  const float rstd = rsqrtf(fmaxf(tss * inv_n - m1 * m1, 0.f) + eps);
+#pragma unroll
+  for (int i = 0; i < MAXU; ++i) {
+    const int idx = threadIdx.x + i * 256;
+    if (idx < total) {
+      const int r = idx / upr, c4 = idx - r * upr;
+      const int c = g * cpg + c4 * 4;
+      const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 be = __ldg(reinterpret_cast<const float4*>(beta + c));
+      const float2 f0 = unpack_bf16x2(u[i].x), f1 = unpack_bf16x2(u[i].y);
+      float t0 = fmaf((f0.x - mean) * rstd, ga.x, be.x), t1 = fmaf((f0.y - mean) * rstd, ga.y, be.y);
+      float t2 = fmaf((f1.x - mean) * rstd, ga.z, be.z), t3 = fmaf((f1.y - mean) * rstd, ga.w, be.w);
+      if (silu) { t0 = silu_fast(t0); t1 = silu_fast(t1); t2 = silu_fast(t2); t3 = silu_fast(t3); }
+      *reinterpret_cast<uint2*>(yb + (long long)r * ldy + c4 * 4) = make_uint2(pack_bf16x2(t0, t1), pack_bf16x2(t2, t3));
+    }
+  }
+}
+
 // ---- LayerNorm: one warp per row, two-pass in registers ----------------------------------------
 template <int MAXV>
 __global__ void ln_kernel(const bf16* __restrict__ x, long long x_batch, bf16* __restrict__ y, long long y_batch,
@@ -330,6 +396,20 @@ extern "C" int glg_groupnorm(const void* x, int64_t ldx, void* y, int64_t ldy, c
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static int small_mode = -1;        // GLG_GN_SMALL=0: the barrier kernel also for H*W <= 256 (measured slower there: 19 vs 15 us)
   if (small_mode < 0) { const char* e = getenv("GLG_GN_SMALL"); small_mode = e ? atoi(e) : 1; }
+  {
+    // register-resident path: the (group, sample) slab fits 256 threads x 20 eight-byte units, rows and group starts 8-byte aligned
+    const int cpg = C / groups;
+    const long long units = (long long)HW * (cpg / 4);
+    if (small_mode && cpg % 4 == 0 && units <= 256 * 20 && !(((uintptr_t)x | (uintptr_t)y) & 7) && (C % 4 == 0)) {
+      dim3 grid(groups, B);
+      const bf16* xp = (const bf16*)x; bf16* yp = (bf16*)y;
+      if (units <= 256 * 5) launch_k(gn_reg_kernel<5>, dim3(grid), dim3(256), 0, st, 1, xp, ldx, yp, ldy, gamma, beta, HW, C, groups, eps, silu);
+      else if (units <= 256 * 10) launch_k(gn_reg_kernel<10>, dim3(grid), dim3(256), 0, st, 1, xp, ldx, yp, ldy, gamma, beta, HW, C, groups, eps, silu);
+      else launch_k(gn_reg_kernel<20>, dim3(grid), dim3(256), 0, st, 1, xp, ldx, yp, ldy, gamma, beta, HW, C, groups, eps, silu);
+      count_launch();
+      return check_launch("gn_reg launch");
+    }
+  }
   if (small_mode && HW <= 256 && ((C / groups) % 2 == 0)) {
     dim3 grid(groups, B);
     launch_k(gn_small_kernel, dim3(grid), dim3(256), 0, st, 1, (const bf16*)x, ldx, (bf16*)y, ldy, gamma, beta, HW, C, groups, eps, silu);
