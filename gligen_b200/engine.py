@@ -37,6 +37,7 @@ class Plan:
         self.static_sig = None      # identity of the inputs the static (timestep-invariant) steps were last run for
         self.inp: Dict[str, torch.Tensor] = {}
         self.out: Optional[torch.Tensor] = None
+        self.buffers: List[torch.Tensor] = []     # every device allocation of this plan (inputs, output, workspace)
         self.graphs: Dict[bool, object] = {}
         self.warm: Dict[bool, int] = {}
         self.nlaunch: Dict[bool, int] = {}
@@ -67,6 +68,7 @@ class Engine:
         self.use_graphs = use_graphs and self.dev.type == "cuda"
         self.loaded = False
         self.weights_version = 0
+        self._plan_allocs: List[torch.Tensor] = []
         self.kernel_launches = 0       # kernels of libgligen_b200.so executed on behalf of this engine (graph replays included)
         # (prefix of every SpatialTransformer, in execution order) -> index into the gate table
         self.st_prefixes = [ly.prefix for blk in self.blocks for ly in blk.layers if ly.kind == "st"]
@@ -258,7 +260,14 @@ class Engine:
     # plan construction
     # ------------------------------------------------------------------------------------------
     def _buf(self, numel: int, dtype=None) -> torch.Tensor:
-        return torch.empty(max(int(numel), 8), device=self.dev, dtype=dtype or self.adt)
+        t = torch.empty(max(int(numel), 8), device=self.dev, dtype=dtype or self.adt)
+        self._plan_allocs.append(t)          # every buffer a plan touches is known by base address (gligen_b200/export.py)
+        return t
+
+    def _zeros(self, *shape, dtype=torch.float32) -> torch.Tensor:
+        t = torch.zeros(*shape, device=self.dev, dtype=dtype)
+        self._plan_allocs.append(t)
+        return t
 
     def _sizes(self, Bt: int, N: int, nctx: int) -> Dict[str, int]:
         cfg = self.cfg
@@ -291,10 +300,11 @@ class Engine:
         S = self.n_streams
         G = N * S
         P = Plan()
+        self._plan_allocs = P.buffers = []
         sz = self._sizes(Bt, N, nctx)
         B_ = {k: self._buf(v, torch.float32 if k == "xstat" else None) for k, v in sz.items()}
         B_["blk2"] = self._buf(sz["blk"])
-        stats = torch.zeros(gn_scratch_floats(Bt), device=self.dev, dtype=torch.float32)   # GLG_GN_SCRATCH_FLOATS, barrier counters zeroed once
+        stats = self._zeros(gn_scratch_floats(Bt))   # GLG_GN_SCRATCH_FLOATS, barrier counters zeroed once
         Himg = cfg.image_size
         f32 = torch.float32
 
@@ -305,21 +315,21 @@ class Engine:
             return B_[name][:n].view(*shape)
 
         # ---- static inputs -------------------------------------------------------------------
-        P.inp["x"] = torch.zeros(Bt, cfg.in_channels, Himg, Himg, device=self.dev, dtype=f32)
+        P.inp["x"] = self._zeros(Bt, cfg.in_channels, Himg, Himg)
         if cfg.inpaint_mode:
-            P.inp["extra"] = torch.zeros(Bt, cfg.in_channels + 1, Himg, Himg, device=self.dev, dtype=f32)
-        P.inp["t"] = torch.zeros(Bt, device=self.dev, dtype=torch.int64)
-        P.inp["context"] = torch.zeros(Bt, nctx, cfg.context_dim, device=self.dev, dtype=f32)
+            P.inp["extra"] = self._zeros(Bt, cfg.in_channels + 1, Himg, Himg)
+        P.inp["t"] = self._zeros(Bt, dtype=torch.int64)
+        P.inp["context"] = self._zeros(Bt, nctx, cfg.context_dim)
         if cfg.tokenizer == "keypoint":
-            P.inp["coords"] = torch.zeros(Bt, N, 2, device=self.dev, dtype=f32)
-            P.inp["masks"] = torch.zeros(Bt, N, device=self.dev, dtype=f32)
+            P.inp["coords"] = self._zeros(Bt, N, 2)
+            P.inp["masks"] = self._zeros(Bt, N)
         else:
-            P.inp["coords"] = torch.zeros(Bt, N, 4, device=self.dev, dtype=f32)
-            P.inp["masks"] = torch.zeros(Bt, N, device=self.dev, dtype=f32)
+            P.inp["coords"] = self._zeros(Bt, N, 4)
+            P.inp["masks"] = self._zeros(Bt, N)
             for si in range(S):
-                P.inp[f"feat{si}"] = torch.zeros(Bt, N, cfg.tok_in_dim, device=self.dev, dtype=f32)
-                P.inp[f"fmask{si}"] = torch.zeros(Bt, N, device=self.dev, dtype=f32)
-        P.out = torch.zeros(Bt, cfg.out_channels, Himg, Himg, device=self.dev, dtype=f32)
+                P.inp[f"feat{si}"] = self._zeros(Bt, N, cfg.tok_in_dim)
+                P.inp[f"fmask{si}"] = self._zeros(Bt, N)
+        P.out = self._zeros(Bt, cfg.out_channels, Himg, Himg)
 
         # ---- grounding tokens (PositionNet) -> objs [S, Bt*N, D] -----------------------------
         D = cfg.tok_out_dim
@@ -345,7 +355,7 @@ class Engine:
         temb = self._buf(Bt * cfg.model_channels).view(Bt, cfg.model_channels)
         e1 = self._buf(Bt * ted).view(Bt, ted)
         e2 = self._buf(Bt * ted).view(Bt, ted)
-        emb_all = torch.zeros(Bt, self.emb_total, device=self.dev, dtype=f32)
+        emb_all = self._zeros(Bt, self.emb_total)
         P.add("temb", lambda: ops.timestep_embedding(P.inp["t"], temb))
         P.add("time_embed.0", lambda: ops.gemm(temb, W["time_embed.0.w"], e1, bias=W["time_embed.0.b"], act=ACT_SILU))
         # only SiLU(emb) is ever consumed (openaimodel.py:171-177): fold the SiLU into this epilogue

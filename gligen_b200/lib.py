@@ -60,6 +60,13 @@ SIGNATURES = {
                                       c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "glg_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "glg_softmax_rows": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p]),
+    "glg_engine_load": (c_int, [C.c_char_p, C.POINTER(c_void_p)]),
+    "glg_engine_buffer": (c_int, [c_void_p, C.c_char_p, C.POINTER(c_void_p), C.POINTER(c_int64)]),
+    "glg_engine_write": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int64, c_void_p]),
+    "glg_engine_read": (c_int, [c_void_p, C.c_char_p, c_void_p, c_int64, c_void_p]),
+    "glg_engine_run": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "glg_engine_num_ops": (c_int64, [c_void_p]),
+    "glg_engine_destroy": (c_int, [c_void_p]),
     "glg_sampler_update": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                    c_float, c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_int64, c_void_p]),
 }

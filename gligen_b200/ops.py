@@ -50,6 +50,7 @@ class CudaOps:
         if self.device.type != "cuda":
             raise L.GligenLibraryError("CudaOps needs a CUDA device (there is no CPU fallback)")
         self.lib = L.load()
+        self._c = self.lib           # where op calls go: the library, or a recorder standing in for it (gligen_b200/export.py)
         self.trace = None          # set to a list to record (kind, algorithmic flops, algorithmic bytes) per op call
         # fp32 scratch for split-K GEMMs (8 slabs of the largest small-M output: 8 x 1024 x 2560 floats = 80 MiB)
         self.splitk_ws = torch.empty(8 * 1024 * 2560, device=self.device, dtype=torch.float32)
@@ -126,7 +127,7 @@ class CudaOps:
         else:
             g.stats_out, g.stats_slots, g.stats_slot_stride = None, 0, 0
         g.splitk_ws, g.splitk_ws_bytes = self.splitk_ws.data_ptr(), self.splitk_ws.numel() * 4
-        L.check(self.lib.glg_gemm(C.byref(g), self._stream()), "glg_gemm")
+        L.check(self._c.glg_gemm(C.byref(g), self._stream()), "glg_gemm")
         taps = 9 if conv is not None else 1
         self._note("conv3x3" if conv is not None else "gemm", 2.0 * M * N * K * taps,
                    2.0 * (M * K + N * K * taps + M * No) + (2.0 * M * No if residual is not None else 0.0))
@@ -144,7 +145,7 @@ class CudaOps:
         a.q_batch, a.k_batch, a.v_batch, a.o_batch = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
         a.B, a.heads, a.d_head, a.Lq, a.Lk = B, heads, d_head, Lq, Lk
         a.scale = float(d_head) ** -0.5
-        L.check(self.lib.glg_attention(C.byref(a), self._stream()), "glg_attention")
+        L.check(self._c.glg_attention(C.byref(a), self._stream()), "glg_attention")
         self._note("attention", 4.0 * B * heads * Lq * Lk * d_head, 2.0 * B * heads * d_head * (2 * Lq + 2 * Lk))
 
     # -- norms ---------------------------------------------------------------------------------------
@@ -153,7 +154,7 @@ class CudaOps:
         B, HW, Cc = x.shape
         xp, _, _, ldx = _rows_view(x)
         yp, _, _, ldy = _rows_view(y)
-        L.check(self.lib.glg_groupnorm(xp, ldx, yp, ldy, gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(),
+        L.check(self._c.glg_groupnorm(xp, ldx, yp, ldy, gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(),
                                        B, HW, Cc, groups, eps, 1 if silu else 0, self._stream()), "glg_groupnorm")
         self._note("groupnorm", 0.0, 2.0 * B * HW * Cc * 3)
 
@@ -161,7 +162,7 @@ class CudaOps:
         """x [B, rows, C] with contiguous rows inside a batch; y likewise (batch strides may differ)."""
         B, rows, Cc = x.shape
         assert x.stride(2) == 1 and x.stride(1) == Cc and y.stride(2) == 1 and y.stride(1) == Cc
-        L.check(self.lib.glg_layernorm(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), gamma.data_ptr(), beta.data_ptr(),
+        L.check(self._c.glg_layernorm(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), gamma.data_ptr(), beta.data_ptr(),
                                        B, rows, Cc, eps, self._stream()), "glg_layernorm")
         self._note("layernorm", 0.0, 2.0 * B * rows * Cc * 2)
 
@@ -173,7 +174,7 @@ class CudaOps:
         if extra is not None:
             assert extra.is_contiguous() and extra.dtype == torch.float32
         op, _, Cout, ldo = _rows_view(out)
-        L.check(self.lib.glg_conv_in(x.data_ptr(), C0, _ptr(extra), C1, w.data_ptr(), bias.data_ptr(), op, ldo,
+        L.check(self._c.glg_conv_in(x.data_ptr(), C0, _ptr(extra), C1, w.data_ptr(), bias.data_ptr(), op, ldo,
                                      B, H, W, Cout, self._stream()), "glg_conv_in")
         self._note("conv_in")
 
@@ -182,7 +183,7 @@ class CudaOps:
         B, _, Cin = x.shape
         xp, _, _, ldx = _rows_view(x)
         assert out.is_contiguous() and out.dtype == torch.float32
-        L.check(self.lib.glg_conv_out(xp, ldx, w.data_ptr(), bias.data_ptr(), out.data_ptr(), B, H, W, Cin, out.shape[1],
+        L.check(self._c.glg_conv_out(xp, ldx, w.data_ptr(), bias.data_ptr(), out.data_ptr(), B, H, W, Cin, out.shape[1],
                                       self._stream()), "glg_conv_out")
         self._note("conv_out")
 
@@ -190,19 +191,19 @@ class CudaOps:
         B, _, Cc = x.shape
         xp, _, _, ldx = _rows_view(x)
         yp, _, _, ldy = _rows_view(y)
-        L.check(self.lib.glg_upsample2x(xp, ldx, yp, ldy, B, H, W, Cc, self._stream()), "glg_upsample2x")
+        L.check(self._c.glg_upsample2x(xp, ldx, yp, ldy, B, H, W, Cc, self._stream()), "glg_upsample2x")
         self._note("upsample2x")
 
     def im2col_s2(self, x, y, H: int, W: int):
         B, _, Cc = x.shape
         xp, _, _, ldx = _rows_view(x)
         assert y.is_contiguous()
-        L.check(self.lib.glg_im2col_s2(xp, ldx, y.data_ptr(), B, H, W, Cc, self._stream()), "glg_im2col_s2")
+        L.check(self._c.glg_im2col_s2(xp, ldx, y.data_ptr(), B, H, W, Cc, self._stream()), "glg_im2col_s2")
         self._note("im2col_s2")
 
     def timestep_embedding(self, t, out):
         assert t.dtype == torch.int64 and out.is_contiguous()
-        L.check(self.lib.glg_timestep_embedding(t.data_ptr(), out.data_ptr(), out.shape[0], out.shape[1], self._stream()),
+        L.check(self._c.glg_timestep_embedding(t.data_ptr(), out.data_ptr(), out.shape[0], out.shape[1], self._stream()),
                 "glg_timestep_embedding")
         self._note("timestep_embedding")
 
@@ -214,7 +215,7 @@ class CudaOps:
         for t in (feat, feat_mask, null_feat, coords, pos_mask, null_pos):
             assert t.is_contiguous() and t.dtype == torch.float32
         assert out.is_contiguous()
-        L.check(self.lib.glg_position_features(feat.data_ptr(), fbs, feat_mask.data_ptr(), null_feat.data_ptr(), coords.data_ptr(),
+        L.check(self._c.glg_position_features(feat.data_ptr(), fbs, feat_mask.data_ptr(), null_feat.data_ptr(), coords.data_ptr(),
                                                pos_mask.data_ptr(), null_pos.data_ptr(), out.data_ptr(), out.shape[-1],
                                                B, N, F_, nc, freqs, self._stream()), "glg_position_features")
         self._note("position_features")
@@ -222,21 +223,21 @@ class CudaOps:
     def softmax_rows(self, s, p, scale: float):
         """s fp32 [rows, cols] (row stride free) -> p bf16 [rows, cols] = softmax(scale * s) along the last dim."""
         assert s.dtype == torch.float32 and s.dim() == 2 and s.stride(1) == 1 and p.dim() == 2 and p.stride(1) == 1 and p.shape == s.shape
-        L.check(self.lib.glg_softmax_rows(s.data_ptr(), s.stride(0), p.data_ptr(), p.stride(0), s.shape[0], s.shape[1], float(scale), self._stream()),
+        L.check(self._c.glg_softmax_rows(s.data_ptr(), s.stride(0), p.data_ptr(), p.stride(0), s.shape[0], s.shape[1], float(scale), self._stream()),
                 "glg_softmax_rows")
         self._note("softmax_rows", 0.0, 6.0 * s.numel())
 
     def cast(self, x, y):
         """fp32 -> activation dtype, contiguous."""
         assert x.is_contiguous() and y.is_contiguous() and x.dtype == torch.float32 and x.numel() == y.numel()
-        L.check(self.lib.glg_cast_f32_bf16(x.data_ptr(), y.data_ptr(), x.numel(), self._stream()), "glg_cast_f32_bf16")
+        L.check(self._c.glg_cast_f32_bf16(x.data_ptr(), y.data_ptr(), x.numel(), self._stream()), "glg_cast_f32_bf16")
         self._note("cast_f32_bf16")
 
     def sampler_update(self, x, e_cond, e_uncond, guidance, olds, coefs, a_t, a_prev, e_out, x_prev):
         o = list(olds) + [None] * (3 - len(olds))
         for t in (x, e_cond, x_prev):
             assert t.is_contiguous() and t.dtype == torch.float32
-        L.check(self.lib.glg_sampler_update(x.data_ptr(), e_cond.data_ptr(), _ptr(e_uncond), float(guidance),
+        L.check(self._c.glg_sampler_update(x.data_ptr(), e_cond.data_ptr(), _ptr(e_uncond), float(guidance),
                                             _ptr(o[0]), _ptr(o[1]), _ptr(o[2]),
                                             float(coefs[0]), float(coefs[1]), float(coefs[2]), float(coefs[3]),
                                             float(a_t), float(a_prev), _ptr(e_out), x_prev.data_ptr(), x.numel(), self._stream()),

@@ -177,6 +177,23 @@ int glg_sampler_update(const float* x, const float* e_cond, const float* e_uncon
                        float c0, float c1, float c2, float c3,
                        float a_t, float a_prev, float* e_out, float* x_prev, int64_t n, void* stream);
 
+/* ---- engine level: a whole UNet forward from an exported plan ----------------------------------
+ * Replaces UNetModel.forward (openaimodel.py:420-464) for hosts that cannot embed Python.  gligen_b200/export.py writes one
+ * (batch rows, grounding slots, context length) plan of the engine to a file: packed weights, workspace sizes and the ordered
+ * op-level calls above with every pointer as (buffer, offset).  Named buffers: inputs "in:x" fp32 [rows,C,H,W], "in:t" int64
+ * [rows], "in:context" fp32 [rows,77,768], "in:coords" / "in:masks" / "in:feat0" / "in:fmask0" (/ "in:feat1" / "in:fmask1",
+ * "in:extra") as GroundingNetInput.prepare lays them out, "out" fp32 [rows,C,H,W]; weights "W:<name>" ("W:gates" holds
+ * scale * tanh(alpha) per fuser, "W:conv_in.w" / "W:conv_in.b" the first conv that restore_first_conv_from_SD swaps).
+ * Not thread-safe per handle; all work is enqueued on `stream`; CUDA-graph capturable (no allocation inside run). */
+typedef struct GlgEngine GlgEngine;
+int glg_engine_load(const char* path, GlgEngine** out);
+int glg_engine_buffer(GlgEngine* e, const char* name, void** dev_ptr, int64_t* bytes);
+int glg_engine_write(GlgEngine* e, const char* name, const void* src, int64_t bytes, void* stream);   /* host or device src */
+int glg_engine_read(GlgEngine* e, const char* name, void* dst, int64_t bytes, void* stream);
+int glg_engine_run(GlgEngine* e, int32_t static_part, int32_t fuser_on, void* stream);
+int64_t glg_engine_num_ops(GlgEngine* e);
+int glg_engine_destroy(GlgEngine* e);
+
 #ifdef __cplusplus
 }
 #endif
