@@ -242,7 +242,7 @@ __global__ void upsample2x_kernel(const bf16* __restrict__ x, long long ldx, bf1
   }
 }
 
-__global__ void im2col_s2_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, int B, int H, int W, int C) {
+__global__ void im2col_s2_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, int B, int H, int W, int C, int pad_lo) {
   pdl_trigger();
   pdl_wait();
   const int vec = C >> 3;
@@ -255,7 +255,7 @@ __global__ void im2col_s2_kernel(const bf16* __restrict__ x, long long ldx, bf16
     const long long pix = t / 9;
     const int xo = (int)(pix % Wo), yo = (int)((pix / Wo) % Ho);
     const int b = (int)(pix / ((long long)Wo * Ho));
-    const int yy = 2 * yo + tap / 3 - 1, xx = 2 * xo + tap % 3 - 1;
+    const int yy = 2 * yo + tap / 3 - pad_lo, xx = 2 * xo + tap % 3 - pad_lo;
     uint4 u = make_uint4(0, 0, 0, 0);
     if (yy >= 0 && yy < H && xx >= 0 && xx < W)
       u = __ldg(reinterpret_cast<const uint4*>(x + (((long long)b * H + yy) * W + xx) * ldx + cv * 8));
@@ -456,12 +456,17 @@ extern "C" int glg_upsample2x(const void* x, int64_t ldx, void* y, int64_t ldy, 
   return check_launch("upsample2x launch");
 }
 
-extern "C" int glg_im2col_s2(const void* x, int64_t ldx, void* y, int32_t B, int32_t H, int32_t Wd, int32_t C, void* stream) {
+extern "C" int glg_im2col_s2_pad(const void* x, int64_t ldx, void* y, int32_t B, int32_t H, int32_t Wd, int32_t C, int32_t pad_lo, void* stream) {
   if (C % 8 || ldx % 8 || (H & 1) || (Wd & 1)) return set_error("glg_im2col_s2: C % 8, even H/W required");
+  if (pad_lo != 0 && pad_lo != 1) return set_error("glg_im2col_s2_pad: pad_lo must be 0 (pad right/bottom only) or 1 (symmetric)");
   const long long total = (long long)B * (H / 2) * (Wd / 2) * 9 * (C / 8);
-  launch_k(im2col_s2_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, ST, 1, (const bf16*)x, ldx, (bf16*)y, B, H, Wd, C);
+  launch_k(im2col_s2_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, ST, 1, (const bf16*)x, ldx, (bf16*)y, B, H, Wd, C, pad_lo);
   count_launch();
   return check_launch("im2col_s2 launch");
+}
+
+extern "C" int glg_im2col_s2(const void* x, int64_t ldx, void* y, int32_t B, int32_t H, int32_t Wd, int32_t C, void* stream) {
+  return glg_im2col_s2_pad(x, ldx, y, B, H, Wd, C, 1, stream);
 }
 
 extern "C" int glg_copy_rows(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int32_t C, void* stream) {

@@ -92,6 +92,7 @@ int dispatch(const EOp& op, void* st) {
     return glg_conv_out(A_P(0), A_I(1), (const float*)A_P(2), (const float*)A_P(3), (float*)A_P(4), A_I32(5), A_I32(6), A_I32(7), A_I32(8), A_I32(9), st);
   if (n == "glg_upsample2x") return glg_upsample2x(A_P(0), A_I(1), A_P(2), A_I(3), A_I32(4), A_I32(5), A_I32(6), A_I32(7), st);
   if (n == "glg_im2col_s2") return glg_im2col_s2(A_P(0), A_I(1), A_P(2), A_I32(3), A_I32(4), A_I32(5), A_I32(6), st);
+  if (n == "glg_im2col_s2_pad") return glg_im2col_s2_pad(A_P(0), A_I(1), A_P(2), A_I32(3), A_I32(4), A_I32(5), A_I32(6), A_I32(7), st);
   if (n == "glg_timestep_embedding") return glg_timestep_embedding((const int64_t*)A_P(0), A_P(1), A_I32(2), A_I32(3), st);
   if (n == "glg_position_features")
     return glg_position_features((const float*)A_P(0), A_I(1), (const float*)A_P(2), (const float*)A_P(3), (const float*)A_P(4), (const float*)A_P(5),

@@ -194,11 +194,14 @@ class CudaOps:
         L.check(self._c.glg_upsample2x(xp, ldx, yp, ldy, B, H, W, Cc, self._stream()), "glg_upsample2x")
         self._note("upsample2x")
 
-    def im2col_s2(self, x, y, H: int, W: int):
+    def im2col_s2(self, x, y, H: int, W: int, pad_lo: int = 1):
         B, _, Cc = x.shape
         xp, _, _, ldx = _rows_view(x)
         assert y.is_contiguous()
-        L.check(self._c.glg_im2col_s2(xp, ldx, y.data_ptr(), B, H, W, Cc, self._stream()), "glg_im2col_s2")
+        if pad_lo == 1:
+            L.check(self._c.glg_im2col_s2(xp, ldx, y.data_ptr(), B, H, W, Cc, self._stream()), "glg_im2col_s2")
+        else:
+            L.check(self._c.glg_im2col_s2_pad(xp, ldx, y.data_ptr(), B, H, W, Cc, pad_lo, self._stream()), "glg_im2col_s2_pad")
         self._note("im2col_s2")
 
     def timestep_embedding(self, t, out):

@@ -358,6 +358,7 @@ class VAEDecoderConfig:
     z_channels: int = 4
     embed_dim: int = 4
     out_ch: int = 3
+    in_channels: int = 3                  # encoder input (ddconfig.in_channels)
     latent_size: int = 64                 # decode(z) with z of shape [B, embed_dim, latent_size, latent_size]
     scale_factor: float = 0.18215         # AutoencoderKL(scale_factor=...), configs/*: decode divides by it
 
@@ -423,6 +424,69 @@ def vae_decoder_param_shapes(cfg: VAEDecoderConfig) -> "OrderedDict[str, tuple]"
     norm("decoder.norm_out", cfg.ch * cfg.ch_mult[0])
     conv("decoder.conv_out", cfg.ch * cfg.ch_mult[0], cfg.out_ch, 3)
     return p
+
+
+def vae_encoder_param_shapes(cfg: VAEDecoderConfig) -> "OrderedDict[str, tuple]":
+    """Keys / shapes of `encoder.*` and `quant_conv.*` (the inpainting front end: model.py:368-432,
+    autoencoder.py:24-38).  attn_resolutions is empty in every shipped config: the only attention is mid.attn_1."""
+    p: "OrderedDict[str, tuple]" = OrderedDict()
+
+    def conv(prefix, cin, cout, k):
+        p[prefix + ".weight"] = (cout, cin, k, k)
+        p[prefix + ".bias"] = (cout,)
+
+    def norm(prefix, c):
+        p[prefix + ".weight"] = (c,)
+        p[prefix + ".bias"] = (c,)
+
+    def resblock(prefix, cin, cout):
+        norm(prefix + ".norm1", cin)
+        conv(prefix + ".conv1", cin, cout, 3)
+        norm(prefix + ".norm2", cout)
+        conv(prefix + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(prefix + ".nin_shortcut", cin, cout, 1)
+
+    conv("encoder.conv_in", cfg.in_channels, cfg.ch, 3)
+    in_mult = (1,) + tuple(cfg.ch_mult)
+    block_in = cfg.ch
+    for i_level in range(len(cfg.ch_mult)):
+        block_in = cfg.ch * in_mult[i_level]
+        block_out = cfg.ch * cfg.ch_mult[i_level]
+        for i_block in range(cfg.num_res_blocks):
+            resblock(f"encoder.down.{i_level}.block.{i_block}", block_in, block_out)
+            block_in = block_out
+        if i_level != len(cfg.ch_mult) - 1:
+            conv(f"encoder.down.{i_level}.downsample.conv", block_in, block_in, 3)
+    resblock("encoder.mid.block_1", block_in, block_in)
+    norm("encoder.mid.attn_1.norm", block_in)
+    for nm in ("q", "k", "v", "proj_out"):
+        conv(f"encoder.mid.attn_1.{nm}", block_in, block_in, 1)
+    resblock("encoder.mid.block_2", block_in, block_in)
+    norm("encoder.norm_out", block_in)
+    conv("encoder.conv_out", block_in, 2 * cfg.z_channels, 3)
+    conv("quant_conv", 2 * cfg.z_channels, 2 * cfg.embed_dim, 1)
+    return p
+
+
+def _draw(shapes, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = OrderedDict()
+    for key, shape in shapes.items():
+        if key.endswith(".bias"):
+            t = torch.randn(shape, generator=g) * 0.05
+        elif len(shape) == 1:
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:
+            fan_in = shape[1] * shape[2] * shape[3]
+            t = torch.randn(shape, generator=g) * (fan_in ** -0.5)
+        sd[key] = t
+    return sd
+
+
+def synthetic_vae_encoder_state_dict(cfg: VAEDecoderConfig, seed: int = 1) -> Dict[str, torch.Tensor]:
+    """Seeded fp32 CPU weights for the encoder half (its own generator: the decoder fixtures do not move)."""
+    return _draw(vae_encoder_param_shapes(cfg), seed)
 
 
 def synthetic_vae_state_dict(cfg: VAEDecoderConfig, seed: int = 0) -> Dict[str, torch.Tensor]:

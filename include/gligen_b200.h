@@ -149,6 +149,9 @@ int glg_conv_out(const void* x, int64_t ldx, const float* w, const float* bias, 
 int glg_upsample2x(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t B, int32_t H, int32_t Wd, int32_t C, void* stream);
 /* im2col for the 3x3 stride-2 pad-1 downsample conv (openaimodel.py:104-106): y[B*Ho*Wo, 9*C], k = tap*C + c. */
 int glg_im2col_s2(const void* x, int64_t ldx, void* y, int32_t B, int32_t H, int32_t Wd, int32_t C, void* stream);
+/* same with the zero padding chosen: pad_lo = 1 is glg_im2col_s2; pad_lo = 0 pads only right / bottom, which is the VAE
+ * encoder's Downsample (ldm/modules/diffusionmodules/model.py:73-77: F.pad (0,1,0,1) then 3x3 stride-2 pad-0). */
+int glg_im2col_s2_pad(const void* x, int64_t ldx, void* y, int32_t B, int32_t H, int32_t Wd, int32_t C, int32_t pad_lo, void* stream);
 /* strided 2-D copy of bf16 rows: y[r, 0:C] = x[r, 0:C] (used to place skip tensors; C % 8 == 0). */
 int glg_copy_rows(const void* x, int64_t ldx, void* y, int64_t ldy, int64_t rows, int32_t C, void* stream);
 /* timestep_embedding (util.py:160-180): out bf16 [B, dim] = [cos(t f) | sin(t f)], f_k = exp(-ln(1e4) k / (dim/2)). */

@@ -302,11 +302,56 @@ def run_vae(name, B, seed=3, store_half=False):
                os.path.join(GOLD, f"{name}_B{B}.pt"))
 
 
+def run_vae_encode(name, B, seed=5, store_half=False):
+    """SURVEY 8(f) rank 3 (encoder half): pin oracle/vae_oracle.vae_encode_moments / vae_encode against the reference
+    AutoencoderKL.encode (same synthetic weights, same image, same global CPU seed for the posterior noise)."""
+    from gligen_b200.spec import NAMED_VAE_CONFIGS, synthetic_vae_encoder_state_dict, vae_encoder_param_shapes
+    from oracle import vae_oracle as VO
+    from ldm.models.autoencoder import AutoencoderKL
+    assert "/root/reference" in sys.modules[AutoencoderKL.__module__].__file__
+    cfg = NAMED_VAE_CONFIGS[name]
+    dd = dict(double_z=True, z_channels=cfg.z_channels, resolution=cfg.image_size, in_channels=cfg.in_channels, out_ch=cfg.out_ch, ch=cfg.ch,
+              ch_mult=list(cfg.ch_mult), num_res_blocks=cfg.num_res_blocks, attn_resolutions=[], dropout=0.0)
+    ref = AutoencoderKL(ddconfig=dd, embed_dim=cfg.embed_dim, scale_factor=cfg.scale_factor).eval()
+    ref_keys = [(k, tuple(v.shape)) for k, v in ref.state_dict().items() if k.startswith(("encoder.", "quant_conv."))]
+    mine = [(k, tuple(s)) for k, s in vae_encoder_param_shapes(cfg).items()]
+    assert ref_keys == mine, "encoder state-dict keys / shapes / registration order differ from the reference"
+    sd = synthetic_vae_encoder_state_dict(cfg, 1)
+    missing, unexpected = ref.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith(("decoder.", "post_quant_conv.")) for k in missing)
+    g = torch.Generator().manual_seed(seed)
+    S = cfg.image_size
+    # a smooth image in [-1, 1] plus texture (what `encode` sees: a normalised RGB picture)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, S), torch.linspace(-1, 1, S), indexing="ij")
+    base = torch.stack([torch.sin(3 * xx + c) * torch.cos(2 * yy - c) for c in range(cfg.in_channels)], 0)
+    x = (0.7 * base[None] + 0.3 * torch.randn(B, cfg.in_channels, S, S, generator=g)).clamp(-1, 1)
+    if store_half:
+        x = x.half().float()               # the fixture stores the image as fp16: run the reference on exactly those values
+    t0 = time.time()
+    with torch.no_grad():
+        mom = ref.quant_conv(ref.encoder(x))
+        torch.manual_seed(1234)
+        z0 = ref.encode(x)
+    t_ref = time.time() - t0
+    mine_mom = VO.vae_encode_moments(cfg, sd, x)
+    torch.manual_seed(1234)
+    mine_z0 = VO.vae_encode(cfg, sd, x)
+    diff = (mom - mine_mom).abs().max().item()
+    diff_z = (z0 - mine_z0).abs().max().item()
+    print(f"{name}: reference encode {tuple(x.shape)} -> {tuple(mom.shape)} in {t_ref:.1f} s; max |oracle - reference| moments {diff:.3e}, "
+          f"sample {diff_z:.3e}; mean |mean| {mom[:, :cfg.embed_dim].abs().mean():.3f}, logvar range [{mom[:, cfg.embed_dim:].min():.2f}, {mom[:, cfg.embed_dim:].max():.2f}]")
+    assert diff <= 1e-4 * max(1.0, mom.abs().max().item()) and diff_z <= 1e-4 * max(1.0, z0.abs().max().item())
+    torch.save({"name": name, "B": B, "seed": seed, "noise_seed": 1234, "x": x.half() if store_half else x, "moments": mom, "z0": z0,
+                "oracle_max_abs_diff": diff},
+               os.path.join(GOLD, f"{name}_enc_B{B}.pt"))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
     ap.add_argument("--tiny", action="store_true")
     ap.add_argument("--vae", action="store_true", help="only the VAE-decoder fixtures (next row, SURVEY 8f)")
+    ap.add_argument("--vae-enc", action="store_true", help="only the VAE-encoder fixtures (SURVEY 8f rank 3, encoder half)")
     ap.add_argument("--configs345", action="store_true", help="full-size single forwards (+ short inpaint loops) for BASELINE configs 3, 4, 5")
     ap.add_argument("--plms50", action="store_true", help="50-step PLMS + CFG final latents at full size (the path the metric is quoted on)")
     args = ap.parse_args()
@@ -317,6 +362,12 @@ if __name__ == "__main__":
         run_vae("tiny_vae64", B=2)
         run_vae("small_vae", B=1, store_half=True)
         run_vae("sd14_vae", B=1, store_half=True)
+        sys.exit(0)
+    if args.vae_enc:
+        run_vae_encode("tiny_vae", B=2)
+        run_vae_encode("tiny_vae64", B=2)
+        run_vae_encode("small_vae", B=1, store_half=True)
+        run_vae_encode("sd14_vae", B=1, store_half=True)
         sys.exit(0)
     if args.configs345:
         # BASELINE config 3 (box + text + image: 30 objects -> 60 grounding tokens), config 5 (keypoint: 8 x 17 = 136

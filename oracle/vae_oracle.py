@@ -8,6 +8,12 @@
     Upsample.forward          model.py:53-57     (nearest x2, then 3x3 conv)
     Normalize                 model.py:38-39     (GroupNorm 32 groups, eps 1e-6)
 
+    AutoencoderKL.encode      autoencoder.py:34-38   Encoder -> quant_conv -> DiagonalGaussianDistribution.sample() * scale_factor
+    Encoder.forward           model.py:434-459
+    Downsample.forward        model.py:73-77         (F.pad (0,1,0,1), then 3x3 stride-2 conv without padding)
+    DiagonalGaussianDistribution  ldm/modules/distributions/distributions.py:24-37 (logvar clamped to [-30, 20]; the noise is
+                              drawn on the CPU with the global generator and moved to the device)
+
 Pinned by oracle/gen_golden.py --vae: executed against the unmodified reference AutoencoderKL with the same synthetic
 weights (measured difference recorded in tests/golden/*_vae_*.pt["oracle_max_abs_diff"]).
 """
@@ -68,3 +74,29 @@ def vae_decode(cfg, sd: Dict[str, torch.Tensor], z: torch.Tensor) -> torch.Tenso
             h = _conv(h, sd, f"decoder.up.{i_level}.upsample.conv", 1)
     h = _swish(_gn(h, sd, "decoder.norm_out"))
     return _conv(h, sd, "decoder.conv_out", 1)
+
+
+@torch.no_grad()
+def vae_encode_moments(cfg, sd: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
+    """x: image [B, in_channels, H, W] in [-1, 1] -> moments [B, 2 * embed_dim, H / 2^(levels-1), ...] (mean | logvar)."""
+    h = _conv(x, sd, "encoder.conv_in", 1)
+    nlev = len(cfg.ch_mult)
+    for i_level in range(nlev):
+        for i_block in range(cfg.num_res_blocks):
+            h = resnet_block(h, sd, f"encoder.down.{i_level}.block.{i_block}")
+        if i_level != nlev - 1:
+            p = f"encoder.down.{i_level}.downsample.conv"
+            h = F.conv2d(F.pad(h, (0, 1, 0, 1)), sd[p + ".weight"], sd[p + ".bias"], stride=2)
+    h = resnet_block(h, sd, "encoder.mid.block_1")
+    h = attn_block(h, sd, "encoder.mid.attn_1")
+    h = resnet_block(h, sd, "encoder.mid.block_2")
+    h = _conv(_swish(_gn(h, sd, "encoder.norm_out")), sd, "encoder.conv_out", 1)
+    return _conv(h, sd, "quant_conv", 0)
+
+
+@torch.no_grad()
+def vae_encode(cfg, sd: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
+    """encode(x): one posterior sample times scale_factor; consumes torch's global CPU generator like the reference."""
+    mean, logvar = torch.chunk(vae_encode_moments(cfg, sd, x), 2, dim=1)
+    std = torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0))
+    return (mean + std * torch.randn(mean.shape).to(x.device)) * cfg.scale_factor

@@ -125,11 +125,12 @@ class RefOps:
         t = t.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
         y.copy_(t.reshape(B, 4 * H * W, C))
 
-    def im2col_s2(self, x, y, H, W):
+    def im2col_s2(self, x, y, H, W, pad_lo=1):
         self.launches += 1
         B, _, C = x.shape
         xin = x.float().reshape(B, H, W, C).permute(0, 3, 1, 2)
-        u = F.unfold(xin, kernel_size=3, padding=1, stride=2)            # [B, C*9, L], (c, tap) ordering
+        xin = F.pad(xin, (pad_lo, 1, pad_lo, 1))                         # even H, W: one zero row / column on the far side
+        u = F.unfold(xin, kernel_size=3, padding=0, stride=2)            # [B, C*9, L], (c, tap) ordering
         L = u.shape[-1]
         u = u.view(B, C, 9, L).permute(0, 3, 2, 1).reshape(B * L, 9 * C)   # -> k = tap*C + c
         y.copy_(u.to(y.dtype))

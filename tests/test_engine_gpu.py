@@ -5,8 +5,10 @@ seeded weights and inputs).
 
 Tolerance (floating point, bf16 operands / fp32 accumulation vs the reference's fp32): the reference's own
 bf16-autocast-vs-fp32 gap for ONE forward is rel-L2 ~1.3e-2, max-abs 0.044 on eps with std 0.56 (SURVEY 6);
-we accept <= 2x that: rel-L2 <= 2.5e-2 and max-abs <= 0.09*max|eps| per forward, and rel-L2 <= 6e-2 on the
-final latent of the short sampling loops (error compounds over sequential forwards)."""
+we accept <= 2x that: rel-L2 <= 2.5e-2 and max-abs <= 0.09*max|eps| per forward, and rel-L2 <= 6e-2 / max-abs <= 10 % of
+max|latent| on the final latent of the SHORT sampling loops (2-5 steps from pure noise, where the iterate is dominated by the
+first evaluations; measured 2.6-4.1e-2 / <= 5.7 %).  The 50-step final latent - the quantity the north star names - has its own
+test with the reference's bf16-autocast gap as the denominator: tests/test_final_latent_gpu.py."""
 import os
 from functools import partial
 
@@ -109,7 +111,7 @@ def run_sampling(name, gold_file, kinds=("plms", "ddim")):
             torch.manual_seed(1234)
             with cpu_rng_noise():
                 lat = sampler.sample(S=g["S"], shape=shape, input=input, uc=inp["uc"].to(DEV), guidance_scale=g["guidance"], mask=mask, x0=z0)
-            r, m = assert_close(lat, g["latent"], rel=6e-2, max_rel=0.2, what=f"{name} {kind} S={g['S']} latent")
+            r, m = assert_close(lat, g["latent"], rel=6e-2, max_rel=0.1, what=f"{name} {kind} S={g['S']} latent")
             print(f"{name} {kind} S={g['S']} alpha={g['alpha_type']}: latent rel_l2={r:.3e} max_rel={m:.3e}")
     finally:
         os.chdir(cwd)

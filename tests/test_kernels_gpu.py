@@ -463,6 +463,14 @@ def test_small_ops(ops, ref):
     col, col_r = torch.zeros(2 * 64, 9 * 640, device=dev, dtype=torch.bfloat16), torch.zeros(2 * 64, 9 * 640, device=dev, dtype=torch.bfloat16)
     ops.im2col_s2(x, col, 16, 16); ref.im2col_s2(x, col_r, 16, 16)
     assert torch.equal(col, col_r)
+    # the VAE encoder's Downsample pads only right / bottom (model.py:73-77)
+    ops.im2col_s2(x, col, 16, 16, pad_lo=0); ref.im2col_s2(x, col_r, 16, 16, pad_lo=0)
+    assert torch.equal(col, col_r)
+    xin = x.float().reshape(2, 16, 16, 640).permute(0, 3, 1, 2)
+    wgt = torch.randn(64, 640, 3, 3, device=dev) * 0.01
+    want = torch.nn.functional.conv2d(torch.nn.functional.pad(xin, (0, 1, 0, 1)), wgt, stride=2)            # the reference's statement
+    got = (col.float() @ wgt.permute(0, 2, 3, 1).reshape(64, -1).t()).reshape(2, 8, 8, 64).permute(0, 3, 1, 2)
+    assert_close(got, want, rel=1e-3, max_rel=5e-3, what="asymmetric-pad stride-2 conv through im2col")
     # timestep embedding
     t = torch.tensor([981, 1, 500, 21], device=dev)
     o, o_r = torch.zeros(4, 320, device=dev, dtype=torch.bfloat16), torch.zeros(4, 320, device=dev, dtype=torch.bfloat16)
