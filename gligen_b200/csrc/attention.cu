@@ -299,9 +299,10 @@ namespace glg {
 int attention_tc(const GlgAttnArgs* a, cudaStream_t st);         // attention_tc.cu: tcgen05 flash attention (streamed key tiles)
 int attention_short_tc(const GlgAttnArgs* a, cudaStream_t st);   // attention_short_tc.cu: tcgen05, all keys in one tile (Lk <= 128)
 int attention_tc2(const GlgAttnArgs* a, cudaStream_t st);        // attention_tc2.cu: tcgen05, key tiles dealt to two independent softmax warpgroups
+int attention_tc3(const GlgAttnArgs* a, cudaStream_t st);        // attention_tc3.cu: tcgen05, one CTA per SM, four softmax warpgroups, one TMEM read per score
 int g_attn_mode = 0;          // test hooks: 0 = auto, 1 = force the mma.sync kernel, 2 = force the streamed tcgen05 kernel,
                               // 3 = force the short-key tcgen05 kernel, 4 = force the two-warpgroup tcgen05 kernel
-                              // (each "where it applies")
+                              // 5 = force the four-warpgroup single-read tcgen05 kernel (each "where it applies")
 }
 
 using namespace glg;
@@ -319,11 +320,15 @@ extern "C" int glg_attention(const GlgAttnArgs* a, void* stream) {
     const int rc = attention_short_tc(a, reinterpret_cast<cudaStream_t>(stream));
     if (rc <= 0) return rc;
   }
-  if ((g_attn_mode == 0 && a->Lk > 128) || g_attn_mode == 4) {      // d_head < 64 with a spare column (d_head = 40: the 64x64 level)
+  if ((g_attn_mode == 0 && a->Lk >= 512) || g_attn_mode == 5) {     // d_head < 64 with a spare column (d_head = 40: the 64x64 level)
+    const int rc = attention_tc3(a, reinterpret_cast<cudaStream_t>(stream));
+    if (rc <= 0) return rc;
+  }
+  if ((g_attn_mode == 0 && a->Lk > 128) || g_attn_mode == 4 || g_attn_mode == 5) {
     const int rc = attention_tc2(a, reinterpret_cast<cudaStream_t>(stream));
     if (rc <= 0) return rc;
   }
-  if ((g_attn_mode == 0 && a->Lk > 128) || g_attn_mode == 2 || g_attn_mode == 4) {
+  if ((g_attn_mode == 0 && a->Lk > 128) || g_attn_mode == 2 || g_attn_mode == 4 || g_attn_mode == 5) {
     const int rc = attention_tc(a, reinterpret_cast<cudaStream_t>(stream));
     if (rc <= 0) return rc;          // 0 = launched, -1 = error; 1 = not applicable -> mma.sync kernel below
   }

@@ -57,7 +57,9 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 // Wait with a watchdog: a protocol bug traps (-> cudaErrorLaunchFailure at the next sync) instead of
 // hanging the GPU box.  The watchdog only runs on the slow path.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+#pragma unroll 1
+  for (int i = 0; i < 256; ++i)           // common case: the phase completes within a few (HW-suspended) polls - no timer read on this path
+    if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = globaltimer_ns();
   while (true) {
 #pragma unroll 1

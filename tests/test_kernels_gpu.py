@@ -296,14 +296,14 @@ ATTN_CASES = [
 
 
 @pytest.mark.parametrize("B,heads,d,Lq,Lk,mode", ATTN_CASES)
-@pytest.mark.parametrize("path", ["auto", "mma_sync", "tcgen05", "tcgen05_sum", "short_tc", "tc2"])
+@pytest.mark.parametrize("path", ["auto", "mma_sync", "tcgen05", "tcgen05_sum", "short_tc", "tc2", "tc3"])
 def test_attention(ops, ref, B, heads, d, Lq, Lk, mode, path):
     """auto: streamed tcgen05 flash kernel (> 128 keys, every d_head <= 160), short-key tcgen05 kernel (<= 128 keys: the
     text context).  Row sums come from a ones column of V when d_head % 16 != 0 (streamed kernel).
     The other paths force the legacy mma.sync kernel / the streamed tcgen05 kernel (also for short key sets) / the
     streamed kernel with the softmax-side row sum."""
-    if path == "tc2" and (d % 16 == 0 or d > 64):
-        pytest.skip("two-warpgroup kernel: d_head < 64 with a spare column for the row sums")
+    if path in ("tc2", "tc3") and (d % 16 == 0 or d > 64):
+        pytest.skip("multi-warpgroup kernels: d_head < 64 with a spare column for the row sums")
     if path == "short_tc" and (Lk > 128 or d > 128 and Lk > 80):
         pytest.skip("short-key kernel: all keys in one tile")
     if path == "short_tc" and Lk <= 128:
@@ -325,7 +325,7 @@ def test_attention(ops, ref, B, heads, d, Lq, Lk, mode, path):
         q, k, v = rnd(B, Lq, C), rnd(B, Lk, C, seed=1), rnd(B, Lk, C, seed=2)
     out = torch.zeros(B, Lq, C, device="cuda:0", dtype=torch.bfloat16)
     out_r = torch.zeros_like(out)
-    ops.lib.glg_debug_attn_mode({"auto": 0, "mma_sync": 1, "tcgen05": 2, "tcgen05_sum": 2, "short_tc": 3, "tc2": 4}[path])
+    ops.lib.glg_debug_attn_mode({"auto": 0, "mma_sync": 1, "tcgen05": 2, "tcgen05_sum": 2, "short_tc": 3, "tc2": 4, "tc3": 5}[path])
     ops.lib.glg_debug_attn_tc_variant(3 if path == "tcgen05_sum" else 0)
     try:
         ops.attention(q, k, v, out, heads, d)
@@ -337,16 +337,19 @@ def test_attention(ops, ref, B, heads, d, Lq, Lk, mode, path):
     assert_close(out, out_r, rel=1e-2, max_rel=5e-2, what=f"attention d={d} {Lq}x{Lk} {mode}")
 
 
+@pytest.mark.parametrize("mode", [4, 5])
 @pytest.mark.parametrize("poly", [1, 2, 3])
-def test_attention_fma_pipe_exp2(ops, ref, poly):
-    """two-warpgroup kernel with `poly` of every 8 score pairs exponentiated on the FMA pipe (Cody-Waite + cubic, rel 1e-4)."""
+def test_attention_fma_pipe_exp2(ops, ref, poly, mode):
+    """multi-warpgroup kernels with `poly` of every 8 score pairs exponentiated on the FMA pipe (Cody-Waite + cubic, rel 1e-4)."""
+    if mode == 5 and poly == 3:
+        pytest.skip("single-read kernel: shares 0..2")
     B, heads, d, Lq, Lk = 2, 8, 40, 1024, 1054
     C = heads * d
     qkv = rnd(B, Lk, 3 * C) * 2.0                   # wider score range than the default cases
     q, k, v = qkv[:, :Lq, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
     out = torch.zeros(B, Lq, C, device="cuda:0", dtype=torch.bfloat16)
     out_r = torch.zeros_like(out)
-    ops.lib.glg_debug_attn_mode(4)
+    ops.lib.glg_debug_attn_mode(mode)
     ops.lib.glg_debug_attn_poly_share(poly)
     try:
         ops.attention(q, k, v, out, heads, d)
