@@ -7,7 +7,7 @@ import torch
 
 from gligen_b200 import checkpoint as CK
 from gligen_b200.pipeline import GROUNDING_INPUT, model_config
-from gligen_b200.spec import NAMED_CONFIGS, NAMED_VAE_CONFIGS, synthetic_state_dict, synthetic_vae_state_dict
+from gligen_b200.spec import NAMED_CONFIGS, NAMED_VAE_CONFIGS, synthetic_state_dict, synthetic_vae_encoder_state_dict, synthetic_vae_state_dict
 
 REF = "/root/reference"
 
@@ -28,7 +28,7 @@ def test_checkpoint_round_trip(tmp_path):
     cfg, v = NAMED_CONFIGS["tiny"], NAMED_VAE_CONFIGS["tiny_vae64"]
     sd = synthetic_state_dict(cfg, 0)
     vsd = dict(synthetic_vae_state_dict(v, 0))
-    vsd["encoder.conv_in.weight"] = torch.zeros(64, 3, 3, 3)
+    vsd.update(synthetic_vae_encoder_state_dict(v, 1))          # a real checkpoint carries both halves (encoder.* / quant_conv.*)
     path = os.path.join(str(tmp_path), "gligen.pth")
     from ldm.models.diffusion.ldm import LatentDiffusion
     dsd = LatentDiffusion(linear_start=0.00085, linear_end=0.012, timesteps=1000).state_dict()      # schedule buffers, as in a real checkpoint
@@ -38,7 +38,8 @@ def test_checkpoint_round_trip(tmp_path):
     got = model.state_dict()
     assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
     assert model.grounding_tokenizer_input is not None and hasattr(model.grounding_tokenizer_input, "prepare")
-    assert torch.equal(vae.state_dict()["decoder.conv_in.weight"], vsd["decoder.conv_in.weight"])
+    vgot = vae.state_dict()
+    assert set(vgot) == set(vsd) and all(torch.equal(vgot[k], vsd[k]) for k in vsd)
     assert diffusion.num_timesteps == 1000 and config["model"]["target"].endswith("UNetModel")
 
 
