@@ -417,12 +417,16 @@ int attention_tc3(const GlgAttnArgs* a, cudaStream_t st) {
   p.probe = g_attn_probe;
   if (g_attn_tc3_stagger < 0) { const char* e = getenv("GLG_ATTN_STAGGER"); g_attn_tc3_stagger = e ? atoi(e) : 0; }
   p.stagger = g_attn_tc3_stagger;
-  if (g_attn_tc2_poly < 0) { const char* e = getenv("GLG_ATTN_POLY"); g_attn_tc2_poly = e ? atoi(e) : 0; }
+  // FMA-pipe share of the exponentials: measured best at 2 of every 8 score pairs for this kernel (level 0, 2B = 8: 409.6 us
+  // all-MUFU, 391.3 / 389.9 / 405.5 / 437.5 us at 1 / 2 / 3 / 4 of 8; profiles/r2_attention_l0.md).  GLG_ATTN_POLY or the debug
+  // setter override it; the two-warpgroup kernel keeps its own default (0).
+  int poly = g_attn_tc2_poly;
+  if (poly < 0) { const char* e = getenv("GLG_ATTN_POLY"); poly = e ? atoi(e) : 2; }
   switch (dpad) {
     case 16: return launch_attn_tc3<16, 0>(tq, tk, tv, p, a->B, st);
     case 32: return launch_attn_tc3<32, 0>(tq, tk, tv, p, a->B, st);
     case 48:
-      switch (g_attn_tc2_poly) {
+      switch (poly) {
         case 1: return launch_attn_tc3<48, 1>(tq, tk, tv, p, a->B, st);
         case 2: return launch_attn_tc3<48, 2>(tq, tk, tv, p, a->B, st);
         case 3: return launch_attn_tc3<48, 3>(tq, tk, tv, p, a->B, st);
