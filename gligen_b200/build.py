@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libgligen_b200.so")
-SOURCES = ["capi.cu", "engine_capi.cu", "tma_host.cu", "gemm_tc.cu", "attention.cu", "attention_tc.cu", "attention_short_tc.cu", "attention_tc2.cu", "attention_tc3.cu", "norm.cu", "elementwise.cu"]
+SOURCES = ["capi.cu", "engine_capi.cu", "tma_host.cu", "gemm_tc.cu", "attention.cu", "attention_tc.cu", "attention_short_tc.cu", "attention_tc2.cu", "attention_tc3.cu", "norm.cu", "elementwise.cu", "frontend.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

@@ -220,6 +220,8 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ------------------------------------------------------------------ math
 // x * sigmoid(x); __fdividef: 2 ulp, no IEEE-division slow path (a CALL per element in the epilogues)
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// CLIP's activation (transformers "quick_gelu": x * sigmoid(1.702 x))
+__device__ __forceinline__ float quick_gelu_f(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
 // erf(z) ~= z P(z^2) / Q(z^2) on |z| <= 4 (clamped; |erf(4)-1| < 2e-8): own least-squares rational fit,
 // max abs error 3.3e-7 in fp32 (checked against scipy.special.erf), branch-free: 11 FMA + 1 rcp.
 __device__ __forceinline__ float erf_rational(float z) {

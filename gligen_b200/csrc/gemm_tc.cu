@@ -347,6 +347,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, uint32_t tad
         if (p.act == GLG_ACT_SILU) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+        } else if (p.act == GLG_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = gelu_erf_f(v[j]);
+        } else if (p.act == GLG_ACT_QUICK_GELU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = quick_gelu_f(v[j]);
         }
         if (p.gate) {
 #pragma unroll
@@ -453,6 +459,12 @@ __global__ void splitk_reduce_kernel(const GemmKParams p) {
     if (p.act == GLG_ACT_SILU) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+    } else if (p.act == GLG_ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = gelu_erf_f(v[j]);
+    } else if (p.act == GLG_ACT_QUICK_GELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = quick_gelu_f(v[j]);
     }
     if (p.gate) {
 #pragma unroll

@@ -80,6 +80,7 @@ class Engine:
             off += ly.cout
         self.emb_total = off
         self._last_N: Optional[int] = None      # grounding slots of the last grounded call (shape of the null input)
+        self._map_shape: Optional[Tuple[int, int, int]] = None    # spatial modalities: (C, H, W) of the conditioning map
         self.n_streams = 2 if cfg.tokenizer == "text_image" else 1
         self.pos_k = _rup(cfg.tok_feat_dim + cfg.position_dim, 64)
 
@@ -204,6 +205,10 @@ class Engine:
 
     def _pack_position_net(self, sd) -> None:
         cfg, W, pn = self.cfg, self.W, "position_net"
+        if cfg.spatial:                      # ConvNeXt tokenizer + grounding downsampler (gligen_b200/spatial.py)
+            from . import spatial
+            spatial.pack(self, sd)
+            return
 
         def mlp(src: str, dst: str):
             w0 = sd[f"{pn}.{src}.0.weight"].float()
@@ -234,7 +239,14 @@ class Engine:
 
     def set_first_conv(self, weight: torch.Tensor, bias: torch.Tensor) -> None:
         """openaimodel.py:400-413 swaps input_blocks[0][0]; here: repack into the static weight slot."""
-        w = self._f(weight.float().permute(2, 3, 1, 0).reshape(9, weight.shape[1], weight.shape[0]))   # [9][Cin][Cout]
+        weight = weight.float()
+        cin = self.cfg.first_conv_in
+        if weight.shape[1] < cin:
+            # the SD first conv (4 input channels) swapped into a model whose GLIGEN first conv also reads the grounding
+            # downsampler's planes (openaimodel.py:400-413, 441-443: with first_conv_type == "SD" they are not concatenated):
+            # zero weights on those channels state the same thing without changing the plan
+            weight = torch.cat([weight, weight.new_zeros(weight.shape[0], cin - weight.shape[1], 3, 3)], dim=1)
+        w = self._f(weight.permute(2, 3, 1, 0).reshape(9, weight.shape[1], weight.shape[0]))   # [9][Cin][Cout]
         b = self._f(bias)
         if "conv_in.w" in self.W and self.W["conv_in.w"].shape == w.shape:
             self.W["conv_in.w"].copy_(w)          # in place: captured graphs keep pointing at this storage
@@ -320,7 +332,12 @@ class Engine:
             P.inp["extra"] = self._zeros(Bt, cfg.in_channels + 1, Himg, Himg)
         P.inp["t"] = self._zeros(Bt, dtype=torch.int64)
         P.inp["context"] = self._zeros(Bt, nctx, cfg.context_dim)
-        if cfg.tokenizer == "keypoint":
+        if cfg.spatial:
+            P.inp["map"] = self._zeros(Bt, *self._map_shape)          # the conditioning map (null rows: zeros)
+            P.inp["gmask"] = self._zeros(Bt)
+            if cfg.ds_out_dim:
+                P.inp["extra_map"] = self._zeros(Bt, *self._map_shape)   # grounding_extra_input (shared by cond and uncond rows)
+        elif cfg.tokenizer == "keypoint":
             P.inp["coords"] = self._zeros(Bt, N, 2)
             P.inp["masks"] = self._zeros(Bt, N)
         else:
@@ -333,11 +350,18 @@ class Engine:
 
         # ---- grounding tokens (PositionNet) -> objs [S, Bt*N, D] -----------------------------
         D = cfg.tok_out_dim
-        pos_rows = self._buf(Bt * N * self.pos_k).view(Bt * N, self.pos_k)
-        hid1 = self._buf(Bt * N * cfg.tok_hidden).view(Bt * N, cfg.tok_hidden)
-        hid2 = self._buf(Bt * N * cfg.tok_hidden).view(Bt * N, cfg.tok_hidden)
         objs = self._buf(S * Bt * N * D).view(S, Bt * N, D)
-        for si in range(S):
+        ds_planes = None
+        if cfg.spatial:
+            from . import spatial
+            spatial.emit_tokenizer(self, P, Bt, self._map_shape, objs[0])
+            if cfg.ds_out_dim:
+                ds_planes = spatial.emit_downsampler(self, P, Bt)
+        else:
+            pos_rows = self._buf(Bt * N * self.pos_k).view(Bt * N, self.pos_k)
+            hid1 = self._buf(Bt * N * cfg.tok_hidden).view(Bt * N, cfg.tok_hidden)
+            hid2 = self._buf(Bt * N * cfg.tok_hidden).view(Bt * N, cfg.tok_hidden)
+        for si in range(0 if cfg.spatial else S):
             if cfg.tokenizer == "keypoint":
                 feat, fmask = W["pn.table"], P.inp["masks"]
             else:
@@ -491,7 +515,7 @@ class Engine:
                 last = li == len(blk.layers) - 1
                 o = final if last else view(tmp_names[li % 2], Bt, H * H, ly.cout)
                 if ly.kind == "conv_in":
-                    extra = P.inp.get("extra")
+                    extra = P.inp.get("extra") if ds_planes is None else ds_planes
                     P.add("conv_in", lambda o=o, extra=extra: ops.conv_in(P.inp["x"], extra, W["conv_in.w"], W["conv_in.b"], o))
                 elif ly.kind == "res":
                     emit_res(ly, h, o, H)
@@ -520,18 +544,29 @@ class Engine:
         return self.plans[key]
 
     def _n_objs(self, grounding: Dict[str, torch.Tensor]) -> int:
+        if self.cfg.spatial:
+            from .spec import SPATIAL_MAP_KEY
+            shape = tuple(grounding[SPATIAL_MAP_KEY[self.cfg.tokenizer]].shape[1:])
+            if shape != self._map_shape:            # static buffers are sized for the map: a new size means new plans
+                self._map_shape = shape
+                self.plans.clear()
+            return self.cfg.spatial_tokens
         return (grounding["points"] if self.cfg.tokenizer == "keypoint" else grounding["boxes"]).shape[1]
 
     def _stage_grounding(self, P: Plan, grounding: Optional[Dict[str, torch.Tensor]], lo: int, hi: int) -> None:
         """Copy grounding kwargs (GroundingNetInput.prepare output) into rows [lo, hi) of the static inputs;
         None -> the null input (all zeros, grounding_input/*:get_null_input)."""
         cfg = self.cfg
-        names = [k for k in P.inp if k in ("coords", "masks") or k.startswith(("feat", "fmask"))]
+        names = [k for k in P.inp if k in ("coords", "masks", "map", "gmask") or k.startswith(("feat", "fmask"))]
         if grounding is None:
             for k in names:
                 P.inp[k][lo:hi].zero_()
             return
-        if cfg.tokenizer == "keypoint":
+        if cfg.spatial:
+            from .spec import SPATIAL_MAP_KEY
+            P.inp["map"][lo:hi].copy_(grounding[SPATIAL_MAP_KEY[cfg.tokenizer]])
+            P.inp["gmask"][lo:hi].copy_(grounding["mask"])
+        elif cfg.tokenizer == "keypoint":
             P.inp["coords"][lo:hi].copy_(grounding["points"])
             P.inp["masks"][lo:hi].copy_(grounding["masks"])
         elif cfg.tokenizer == "text":
@@ -621,21 +656,29 @@ class Engine:
         return t[lo:hi]
 
     @torch.no_grad()
-    def forward(self, x, timesteps, context, grounding, inpainting_extra_input=None) -> torch.Tensor:
+    def forward(self, x, timesteps, context, grounding, inpainting_extra_input=None, grounding_extra_input=None) -> torch.Tensor:
         """One UNet pass (UNetModel.forward semantics).  grounding=None -> null grounding tokens.
+        grounding_extra_input: the map the grounding downsampler reads (spatial modalities; None -> zero planes).
         Returns a NEW fp32 tensor [B, out_channels, H, W]."""
         assert self.loaded, "load_state_dict first"
         B = x.shape[0]
         if B <= self.MAX_ROWS:
-            return self._forward_rows(x, timesteps, context, grounding, inpainting_extra_input, 0).clone()
+            return self._forward_rows(x, timesteps, context, grounding, inpainting_extra_input, 0, grounding_extra_input).clone()
         outs = []
         for slot, lo in enumerate(range(0, B, self.MAX_ROWS)):
             hi = min(B, lo + self.MAX_ROWS)
             outs.append(self._forward_rows(x[lo:hi], timesteps[lo:hi], context[lo:hi], self._rows(grounding, lo, hi),
-                                           self._rows(inpainting_extra_input, lo, hi), slot).clone())
+                                           self._rows(inpainting_extra_input, lo, hi), slot, self._rows(grounding_extra_input, lo, hi)).clone())
         return torch.cat(outs, 0)
 
-    def _forward_rows(self, x, timesteps, context, grounding, inpainting_extra_input, slot):
+    def _stage_extra_map(self, P: Plan, gextra, lo: int, hi: int) -> None:
+        if "extra_map" in P.inp:
+            if gextra is None:
+                P.inp["extra_map"][lo:hi].zero_()
+            else:
+                P.inp["extra_map"][lo:hi].copy_(gextra)
+
+    def _forward_rows(self, x, timesteps, context, grounding, inpainting_extra_input, slot, grounding_extra_input=None):
         B = x.shape[0]
         if grounding is not None:
             N = self._last_N = self._n_objs(grounding)
@@ -649,15 +692,16 @@ class Engine:
         P.inp["t"].copy_(timesteps)
         if self.cfg.inpaint_mode:
             P.inp["extra"].copy_(inpainting_extra_input)
-        sig = ("single", self._sig(context, grounding), self.weights_version)
+        sig = ("single", self._sig(context, grounding, grounding_extra_input), self.weights_version)
         if P.static_sig != sig:
             P.inp["context"].copy_(context)
             self._stage_grounding(P, grounding, 0, B)
-        self._execute(P, sig, (context, grounding))
+            self._stage_extra_map(P, grounding_extra_input, 0, B)
+        self._execute(P, sig, (context, grounding, grounding_extra_input))
         return P.out
 
     @torch.no_grad()
-    def forward_cfg(self, x, timesteps, context, uc, grounding, inpainting_extra_input=None):
+    def forward_cfg(self, x, timesteps, context, uc, grounding, inpainting_extra_input=None, grounding_extra_input=None):
         """cond + uncond (null grounding, context = uc) as ONE 2B-row pass.  Returns (eps_cond, eps_uncond)
         as views of the static output (valid until the next call); batches above MAX_ROWS / 2 images run in chunks
         and return new tensors."""
@@ -665,16 +709,16 @@ class Engine:
         B = x.shape[0]
         per = self.MAX_ROWS // 2
         if B <= per:
-            return self._forward_cfg_rows(x, timesteps, context, uc, grounding, inpainting_extra_input, 0)
+            return self._forward_cfg_rows(x, timesteps, context, uc, grounding, inpainting_extra_input, 0, grounding_extra_input)
         conds, unconds = [], []
         for slot, lo in enumerate(range(0, B, per)):
             hi = min(B, lo + per)
             c, u = self._forward_cfg_rows(x[lo:hi], timesteps[lo:hi], context[lo:hi], uc[lo:hi], self._rows(grounding, lo, hi),
-                                          self._rows(inpainting_extra_input, lo, hi), slot)
+                                          self._rows(inpainting_extra_input, lo, hi), slot, self._rows(grounding_extra_input, lo, hi))
             conds.append(c.clone()); unconds.append(u.clone())
         return torch.cat(conds, 0), torch.cat(unconds, 0)
 
-    def _forward_cfg_rows(self, x, timesteps, context, uc, grounding, inpainting_extra_input, slot):
+    def _forward_cfg_rows(self, x, timesteps, context, uc, grounding, inpainting_extra_input, slot, grounding_extra_input=None):
         B = x.shape[0]
         N = self._n_objs(grounding)
         self._last_N = N
@@ -683,10 +727,12 @@ class Engine:
         P.inp["t"][:B].copy_(timesteps); P.inp["t"][B:].copy_(timesteps)
         if self.cfg.inpaint_mode:
             P.inp["extra"][:B].copy_(inpainting_extra_input); P.inp["extra"][B:].copy_(inpainting_extra_input)
-        sig = ("cfg", self._sig(context, uc, grounding), self.weights_version)
+        sig = ("cfg", self._sig(context, uc, grounding, grounding_extra_input), self.weights_version)
         if P.static_sig != sig:
             P.inp["context"][:B].copy_(context); P.inp["context"][B:].copy_(uc)
             self._stage_grounding(P, grounding, 0, B)
             self._stage_grounding(P, None, B, 2 * B)
-        self._execute(P, sig, (context, uc, grounding))
+            self._stage_extra_map(P, grounding_extra_input, 0, B)        # plms.py:118: the uncond pass keeps grounding_extra_input
+            self._stage_extra_map(P, grounding_extra_input, B, 2 * B)
+        self._execute(P, sig, (context, uc, grounding, grounding_extra_input))
         return P.out[:B], P.out[B:]

@@ -223,6 +223,62 @@ class CudaOps:
                                                B, N, F_, nc, freqs, self._stream()), "glg_position_features")
         self._note("position_features")
 
+    # -- spatial grounding modalities (ConvNeXt tokenizer, grounding downsamplers): once per sample -------------
+    def patchify_nchw(self, x, out, Hv: int, Wv: int, k: int):
+        """x fp32 [B, C, Hs, Ws] resampled (nearest) onto Hv x Wv, k x k stride-k patches -> out bf16 [B*(Hv/k)*(Wv/k), ldo]."""
+        B, Cc, Hs, Ws = x.shape
+        assert x.is_contiguous() and x.dtype == torch.float32 and out.is_contiguous() and out.dim() == 2
+        L.check(self._c.glg_patchify_nchw(x.data_ptr(), out.data_ptr(), out.shape[1], B, Cc, Hs, Ws, Hv, Wv, k, self._stream()), "glg_patchify_nchw")
+        self._note("patchify")
+
+    def patchify_nhwc(self, x, out, H: int, W: int, C: int, k: int):
+        """x bf16 rows [B*H*W, ldx] (first C columns used) -> out bf16 [B*(H/k)*(W/k), k*k*C]."""
+        xp, rows, _, ldx = _rows_view(x)
+        assert out.is_contiguous() and out.dim() == 2
+        L.check(self._c.glg_patchify_nhwc(xp, ldx, out.data_ptr(), out.shape[1], rows // (H * W), H, W, C, k, self._stream()), "glg_patchify_nhwc")
+        self._note("patchify")
+
+    def layernorm_rows(self, x, y, gamma, beta, C: int, eps: float):
+        """LayerNorm over the first C columns of each row of x [rows, Cpad]; y columns [C, Cpad) are zeroed."""
+        xp, rows, cp, ldx = _rows_view(x)
+        yp, _, cpy, ldy = _rows_view(y)
+        L.check(self._c.glg_layernorm_rows(xp, ldx, yp, ldy, gamma.data_ptr(), beta.data_ptr(), rows, C, cpy, eps, self._stream()), "glg_layernorm_rows")
+        self._note("layernorm_rows", 0.0, 4.0 * rows * C)
+
+    def dwconv7_ln(self, x, y, w, bias, gamma, beta, B: int, H: int, W: int, C: int, eps: float):
+        """depthwise 7x7 + bias + LayerNorm over the first C channels: x, y bf16 rows [B*H*W, Cpad]; w fp32 [49, C]."""
+        xp, _, _, ldx = _rows_view(x)
+        yp, _, cpy, ldy = _rows_view(y)
+        L.check(self._c.glg_dwconv7_ln(xp, ldx, yp, ldy, w.data_ptr(), bias.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, H, W, C, cpy, eps,
+                                        self._stream()), "glg_dwconv7_ln")
+        self._note("dwconv7_ln", 98.0 * B * H * W * C, 4.0 * B * H * W * C)
+
+    def spatial_tokens(self, x, mask, null_feat, pos, y, n: int):
+        """y[b, t] = x[b, t] * mask[b] + null_feat * (1 - mask[b]) + pos[t]; x, y bf16 [B*n, C]."""
+        xp, rows, Cc, ldx = _rows_view(x)
+        yp, _, _, ldy = _rows_view(y)
+        L.check(self._c.glg_spatial_tokens(xp, ldx, mask.data_ptr(), null_feat.data_ptr(), pos.data_ptr(), yp, ldy, rows // n, n, Cc, self._stream()),
+                "glg_spatial_tokens")
+        self._note("spatial_tokens")
+
+    def resize_plane(self, x, y, C: int, mode: str):
+        """F.interpolate of channels 0..C-1 of x fp32 [B, Cx, Hs, Ws] -> y fp32 [B, C, Ho, Wo]; mode "nearest" | "bicubic"."""
+        assert x.is_contiguous() and y.is_contiguous() and x.dtype == torch.float32 and y.dtype == torch.float32 and y.shape[1] == C
+        L.check(self._c.glg_resize_plane(x.data_ptr(), x.stride(0), y.data_ptr(), x.shape[0], C, x.shape[2], x.shape[3], y.shape[2], y.shape[3],
+                                          {"nearest": 0, "bicubic": 1}[mode], self._stream()), "glg_resize_plane")
+        self._note("resize_plane")
+
+    def conv2d_small(self, x, w, bias, y, k: int, stride: int, pad: int, silu: bool, virtual=None):
+        """Direct Conv2d on fp32 NCHW, Cout in {3, 4, 8, 16}; w fp32 packed [Cin*k*k, Cout]; `virtual=(Hv, Wv)`: the input is x
+        resampled (nearest) onto that grid first."""
+        B, Cin, Hs, Ws = x.shape
+        Hv, Wv = virtual or (Hs, Ws)
+        assert x.is_contiguous() and y.is_contiguous() and w.is_contiguous() and w.shape == (Cin * k * k, y.shape[1])
+        assert y.shape[2] == (Hv + 2 * pad - k) // stride + 1 and y.shape[3] == (Wv + 2 * pad - k) // stride + 1
+        L.check(self._c.glg_conv2d_small(x.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), B, Cin, Hs, Ws, Hv, Wv, y.shape[1], k, stride, pad,
+                                          1 if silu else 0, self._stream()), "glg_conv2d_small")
+        self._note("conv2d_small")
+
     def softmax_rows(self, s, p, scale: float):
         """s fp32 [rows, cols] (row stride free) -> p bf16 [rows, cols] = softmax(scale * s) along the last dim."""
         assert s.dtype == torch.float32 and s.dim() == 2 and s.stride(1) == 1 and p.dim() == 2 and p.stride(1) == 1 and p.shape == s.shape

@@ -17,26 +17,47 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
-from .spec import NAMED_CONFIGS, UNetConfig, synthetic_state_dict
+from .spec import NAMED_CONFIGS, SPATIAL_MAP_KEY, SPATIAL_TOKENIZERS, UNetConfig, synthetic_state_dict
 
 TOKENIZER = {
     "text": ("ldm.modules.diffusionmodules.text_grounding_net.PositionNet", lambda c: dict(in_dim=c.tok_in_dim, out_dim=c.tok_out_dim)),
     "text_image": ("ldm.modules.diffusionmodules.text_image_grounding_net.PositionNet", lambda c: dict(in_dim=c.tok_in_dim, out_dim=c.tok_out_dim)),
     "keypoint": ("ldm.modules.diffusionmodules.keypoint_grounding_net.PositionNet", lambda c: dict(max_persons_per_image=c.max_persons, out_dim=c.tok_out_dim)),
 }
+for _t in SPATIAL_TOKENIZERS:
+    TOKENIZER[_t] = (f"ldm.modules.diffusionmodules.{_t}_grounding_net.PositionNet",
+                     (lambda c: dict(resize_input=c.tok_resize, out_dim=c.tok_out_dim, in_dim=c.sem_in_dim)) if _t == "sem" else
+                     (lambda c: dict(resize_input=c.tok_resize, out_dim=c.tok_out_dim)))
 GROUNDING_INPUT = {"text": "grounding_input.text_grounding_tokinzer_input.GroundingNetInput",
                    "text_image": "grounding_input.text_image_grounding_tokinzer_input.GroundingNetInput",
                    "keypoint": "grounding_input.keypoint_grounding_tokinzer_input.GroundingNetInput"}
 
 
+GROUNDING_INPUT.update({t: f"grounding_input.{t}_grounding_tokinzer_input.GroundingNetInput" for t in SPATIAL_TOKENIZERS})
+GROUNDING_DS_INPUT = {t: f"grounding_input.{t}_grounding_downsampler_input.GroundingDSInput" for t in SPATIAL_TOKENIZERS}
+
+
+def downsampler_config(cfg: UNetConfig) -> Optional[Dict]:
+    """The `grounding_downsampler` entry of configs/cc3m_hed.yaml, cc3m_canny.yaml, cc3m_depth.yaml, diode_normal.yaml, ade_sem.yaml."""
+    if not cfg.ds_out_dim:
+        return None
+    par = dict(out_dim=cfg.ds_out_dim)
+    if cfg.tokenizer != "hed":
+        par["resize_input"] = cfg.ds_resize
+    if cfg.tokenizer == "sem":
+        par["in_dim"] = cfg.sem_in_dim
+    return dict(target=f"ldm.modules.diffusionmodules.{cfg.tokenizer}_grounding_downsampler.GroundingDownsampler", params=par)
+
+
 def model_config(cfg: UNetConfig) -> Dict:
     """The `config['model']` entry a GLIGEN checkpoint carries (configs/*.yaml -> config_dict)."""
     tgt, par = TOKENIZER[cfg.tokenizer]
-    return dict(target="ldm.modules.diffusionmodules.openaimodel.UNetModel", params=dict(
+    extra = {} if not cfg.ds_out_dim else dict(grounding_downsampler=downsampler_config(cfg))
+    return dict(target="ldm.modules.diffusionmodules.openaimodel.UNetModel", params=dict(**extra, **dict(
         image_size=cfg.image_size, in_channels=cfg.in_channels, out_channels=cfg.out_channels, model_channels=cfg.model_channels,
         attention_resolutions=list(cfg.attention_resolutions), num_res_blocks=cfg.num_res_blocks, channel_mult=list(cfg.channel_mult),
         num_heads=cfg.num_heads, transformer_depth=1, context_dim=cfg.context_dim, fuser_type="gatedSA", use_checkpoint=True,
-        inpaint_mode=cfg.inpaint_mode, grounding_tokenizer=dict(target=tgt, params=par(cfg))))
+        inpaint_mode=cfg.inpaint_mode, grounding_tokenizer=dict(target=tgt, params=par(cfg)))))
 
 
 def build_model(name, device="cuda:0", load_weights: bool = True, seed: int = 0):
@@ -89,6 +110,10 @@ def sampler_inputs(cfg: UNetConfig, model, tensors: Dict[str, torch.Tensor], bat
         mask = draw_masks_from_boxes(batch["boxes"], cfg.image_size).to(tensors["x"].device)
         x0 = tensors["z0"]
         extra = torch.cat([x0 * mask, mask], dim=1)
+    gextra = None
+    if cfg.spatial and cfg.ds_out_dim:          # gligen_inference.py:414-416: grounding_downsampler_input.prepare(batch)
+        from ldm.util import instantiate_from_config
+        gextra = instantiate_from_config(dict(target=GROUNDING_DS_INPUT[cfg.tokenizer])).prepare(batch)
     input = dict(x=tensors["x"].clone(), timesteps=None, context=tensors["context"], grounding_input=grounding,
-                 inpainting_extra_input=extra, grounding_extra_input=None)
+                 inpainting_extra_input=extra, grounding_extra_input=gextra)
     return input, mask, x0

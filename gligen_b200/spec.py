@@ -30,13 +30,19 @@ class UNetConfig:
     context_dim: int = 768
     fuser_type: str = "gatedSA"
     inpaint_mode: bool = False
-    # grounding tokenizer: "text" | "text_image" | "keypoint"
+    # grounding tokenizer: "text" | "text_image" | "keypoint" (discrete objects) or one of SPATIAL_TOKENIZERS
+    # ("hed" | "canny" | "depth" | "normal" | "sem": a ConvNeXt-tiny over a spatial map)
     tokenizer: str = "text"
     tok_in_dim: int = 768          # text / text_image: CLIP feature dim
     tok_out_dim: int = 768
     tok_hidden: int = 512          # hard-coded 512 in the reference PositionNets
     fourier_freqs: int = 8
     max_persons: int = 8           # keypoint only
+    # spatial-map modalities (configs/cc3m_hed.yaml, cc3m_canny.yaml, cc3m_depth.yaml, diode_normal.yaml, ade_sem.yaml)
+    tok_resize: int = 256          # PositionNet(resize_input=...): the map is resampled to this size; tokens = (resize / 32)^2
+    sem_in_dim: int = 152          # sem only: one-hot classes (PositionNet / GroundingDownsampler in_dim)
+    ds_out_dim: int = 0            # GroundingDownsampler.out_dim: extra first-conv channels (0 = no downsampler)
+    ds_resize: int = 256           # GroundingDownsampler(resize_input=...) (hed: unused, bicubic straight to the latent size)
 
     @property
     def time_embed_dim(self) -> int:
@@ -44,8 +50,23 @@ class UNetConfig:
 
     @property
     def first_conv_in(self) -> int:
-        # openaimodel.py:299-304
-        return self.in_channels * 2 + 1 if self.inpaint_mode else self.in_channels
+        # openaimodel.py:293-304
+        if self.inpaint_mode:
+            return self.in_channels * 2 + 1 + self.ds_out_dim
+        return self.in_channels + self.ds_out_dim
+
+    @property
+    def spatial(self) -> bool:
+        return self.tokenizer in SPATIAL_TOKENIZERS
+
+    @property
+    def map_channels(self) -> int:
+        """Channels of the spatial conditioning map as the dataset delivers it (grey maps are replicated to RGB)."""
+        return self.sem_in_dim if self.tokenizer == "sem" else 3
+
+    @property
+    def spatial_tokens(self) -> int:
+        return (self.tok_resize // 32) ** 2
 
     @property
     def position_dim(self) -> int:
@@ -58,7 +79,15 @@ class UNetConfig:
         return self.tok_out_dim if self.tokenizer == "keypoint" else self.tok_in_dim
 
     def tokens_per_sample(self, max_objs: int) -> int:
+        if self.spatial:
+            return self.spatial_tokens
         return 2 * max_objs if self.tokenizer == "text_image" else max_objs
+
+
+SPATIAL_TOKENIZERS = ("hed", "canny", "depth", "normal", "sem")
+#: kwarg name of the map in the tokenizer's forward / GroundingNetInput (grounding_input/*_grounding_tokinzer_input.py:19-26)
+SPATIAL_MAP_KEY = {"hed": "hed_edge", "canny": "canny_edge", "depth": "depth", "normal": "normal", "sem": "sem"}
+CONVNEXT_TINY_DEPTHS, CONVNEXT_TINY_DIMS = (3, 3, 9, 3), (96, 192, 384, 768)
 
 
 SD14_BOX_TEXT = UNetConfig()
@@ -71,6 +100,17 @@ TINY = UNetConfig(image_size=16, model_channels=64, context_dim=128, tok_in_dim=
 TINY_TEXT_IMAGE = replace(TINY, tokenizer="text_image")
 TINY_KEYPOINT = replace(TINY, tokenizer="keypoint", max_persons=2)
 TINY_INPAINT = replace(TINY, inpaint_mode=True)
+# spatial-map modalities: the shipped configs (out_dim 768, resize 256 -> 64 tokens; hed adds 1 first-conv channel, the rest 8)
+SD14_HED = replace(SD14_BOX_TEXT, tokenizer="hed", ds_out_dim=1)
+SD14_CANNY = replace(SD14_BOX_TEXT, tokenizer="canny", ds_out_dim=8)
+SD14_DEPTH = replace(SD14_BOX_TEXT, tokenizer="depth", ds_out_dim=8)
+SD14_NORMAL = replace(SD14_BOX_TEXT, tokenizer="normal", ds_out_dim=8)
+SD14_SEM = replace(SD14_BOX_TEXT, tokenizer="sem", ds_out_dim=8)
+# tiny UNets behind the real ConvNeXt-tiny (the backbone has one size); 128-pixel tokenizer input -> 16 tokens
+TINY_HED = replace(TINY, tokenizer="hed", ds_out_dim=1, tok_resize=128, image_size=64)     # hed: bicubic straight to 64 x 64 (hard-coded in the reference)
+TINY_DEPTH = replace(TINY, tokenizer="depth", ds_out_dim=8, tok_resize=128, ds_resize=64)
+TINY_NORMAL = replace(TINY, tokenizer="normal", ds_out_dim=8, tok_resize=128, ds_resize=64)
+TINY_SEM = replace(TINY, tokenizer="sem", ds_out_dim=8, tok_resize=128, ds_resize=64, sem_in_dim=24)
 
 NAMED_CONFIGS = {
     "sd14_box_text": SD14_BOX_TEXT,
@@ -81,6 +121,8 @@ NAMED_CONFIGS = {
     "tiny_text_image": TINY_TEXT_IMAGE,
     "tiny_keypoint": TINY_KEYPOINT,
     "tiny_inpaint": TINY_INPAINT,
+    "sd14_hed": SD14_HED, "sd14_canny": SD14_CANNY, "sd14_depth": SD14_DEPTH, "sd14_normal": SD14_NORMAL, "sd14_sem": SD14_SEM,
+    "tiny_hed": TINY_HED, "tiny_depth": TINY_DEPTH, "tiny_normal": TINY_NORMAL, "tiny_sem": TINY_SEM,
 }
 
 
@@ -275,8 +317,51 @@ def unet_param_shapes(cfg: UNetConfig) -> "OrderedDict[str, tuple]":
         p[f"{pn}.null_person_feature"] = (cfg.tok_out_dim,)
         p[f"{pn}.null_xy_feature"] = (cfg.position_dim,)
         _mlp3(p, f"{pn}.linears", din, cfg.tok_hidden, cfg.tok_out_dim)
+    elif cfg.spatial:
+        # hed_grounding_net.py:13-35 (canny / depth / normal identical; sem adds in_conv, sem_grounding_net.py:21)
+        if cfg.tokenizer == "sem":
+            p[f"{pn}.in_conv.weight"] = (3, cfg.sem_in_dim, 3, 3)
+            p[f"{pn}.in_conv.bias"] = (3,)
+        p.update(convnext_tiny_param_shapes(f"{pn}.convnext_tiny_backbone"))
+        p[f"{pn}.pos_embedding"] = (1, cfg.spatial_tokens, CONVNEXT_TINY_DIMS[-1])
+        _mlp3(p, f"{pn}.linears", CONVNEXT_TINY_DIMS[-1], cfg.tok_hidden, cfg.tok_out_dim)
+        p[f"{pn}.null_feature"] = (CONVNEXT_TINY_DIMS[-1],)
     else:
         raise ValueError(f"unknown tokenizer {cfg.tokenizer!r}")
+    p.update(downsampler_param_shapes(cfg))
+    return p
+
+
+def convnext_tiny_param_shapes(prefix: str) -> "OrderedDict[str, tuple]":
+    """ConvNeXt-tiny without head (convnext.py:53-94, depths 3/3/9/3, dims 96/192/384/768), registration order."""
+    p: "OrderedDict[str, tuple]" = OrderedDict()
+    dims, depths = CONVNEXT_TINY_DIMS, CONVNEXT_TINY_DEPTHS
+    d = f"{prefix}.downsample_layers"
+    p[f"{d}.0.0.weight"], p[f"{d}.0.0.bias"] = (dims[0], 3, 4, 4), (dims[0],)
+    p[f"{d}.0.1.weight"], p[f"{d}.0.1.bias"] = (dims[0],), (dims[0],)
+    for i in range(3):
+        p[f"{d}.{i + 1}.0.weight"], p[f"{d}.{i + 1}.0.bias"] = (dims[i],), (dims[i],)
+        p[f"{d}.{i + 1}.1.weight"], p[f"{d}.{i + 1}.1.bias"] = (dims[i + 1], dims[i], 2, 2), (dims[i + 1],)
+    for i in range(4):
+        for j in range(depths[i]):
+            b, c = f"{prefix}.stages.{i}.{j}", dims[i]
+            p[f"{b}.gamma"] = (c,)
+            p[f"{b}.dwconv.weight"], p[f"{b}.dwconv.bias"] = (c, 1, 7, 7), (c,)
+            p[f"{b}.norm.weight"], p[f"{b}.norm.bias"] = (c,), (c,)
+            p[f"{b}.pwconv1.weight"], p[f"{b}.pwconv1.bias"] = (4 * c, c), (4 * c,)
+            p[f"{b}.pwconv2.weight"], p[f"{b}.pwconv2.bias"] = (c, 4 * c), (c,)
+    return p
+
+
+def downsampler_param_shapes(cfg: UNetConfig) -> "OrderedDict[str, tuple]":
+    """GroundingDownsampler parameters (`downsample_net.*`): hed has none (bicubic only, hed_grounding_downsampler.py:9-21);
+    canny / depth 1->4->out, normal 3->4->out, sem in_dim->16->out, all Conv2d(k=4, s=2, p=1)."""
+    p: "OrderedDict[str, tuple]" = OrderedDict()
+    if not cfg.spatial or cfg.tokenizer == "hed":
+        return p
+    cin, mid = {"canny": (1, 4), "depth": (1, 4), "normal": (3, 4), "sem": (cfg.sem_in_dim, 16)}[cfg.tokenizer]
+    p["downsample_net.layers.0.weight"], p["downsample_net.layers.0.bias"] = (mid, cin, 4, 4), (mid,)
+    p["downsample_net.layers.2.weight"], p["downsample_net.layers.2.bias"] = (cfg.ds_out_dim, mid, 4, 4), (cfg.ds_out_dim,)
     return p
 
 
@@ -301,6 +386,10 @@ def synthetic_state_dict(cfg: UNetConfig, seed: int = 0) -> Dict[str, torch.Tens
             t = 1.0 + 0.1 * torch.randn(shape, generator=g)
         elif key.endswith("_embeddings"):
             t = torch.randn(shape, generator=g)
+        elif key.endswith("pos_embedding"):
+            t = torch.randn(shape, generator=g) * 0.02            # hed_grounding_net.py:25 (BERT-style)
+        elif leaf == "gamma":                                       # ConvNeXt layer scale (1e-6 at init, O(0.1-1) when trained)
+            t = 0.5 + 0.1 * torch.randn(shape, generator=g)
         else:
             fan_in = 1
             for s in shape[1:]:
@@ -337,6 +426,8 @@ def flops_per_forward(cfg: UNetConfig, G: int, fuser_on: bool = True) -> float:
                 total += 18.0 * (hw * 4) * ly.cin * ly.cout
     total += 18.0 * cfg.image_size ** 2 * cfg.model_channels * cfg.out_channels
     total += 2.0 * (cfg.model_channels * ted + ted * ted)
+    if cfg.spatial:
+        return total          # the ConvNeXt tokenizer runs once per sample, not per forward
     din = cfg.tok_feat_dim + cfg.position_dim
     n_mlp = 2 if cfg.tokenizer == "text_image" else 1
     gtok = G // n_mlp

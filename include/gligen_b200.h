@@ -28,6 +28,8 @@ extern "C" {
 
 #define GLG_ACT_NONE 0
 #define GLG_ACT_SILU 1
+#define GLG_ACT_GELU 2        /* exact (erf) GELU: nn.GELU() of the ConvNeXt blocks (convnext.py:32) */
+#define GLG_ACT_QUICK_GELU 3  /* x * sigmoid(1.702 x): the CLIP text encoder's MLP activation */
 
 /* ---- library ------------------------------------------------------------------------------- */
 int glg_abi_version(void);
@@ -169,6 +171,36 @@ int glg_position_features(const float* feat, int64_t feat_batch_stride, const fl
 int glg_softmax_rows(const float* s, int64_t lds, void* p, int64_t ldp, int64_t rows, int32_t cols, float scale, void* stream);
 /* fp32 -> bf16 cast of a contiguous buffer (context / weights staging). */
 int glg_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream);
+
+/* ---- spatial grounding modalities: ConvNeXt tokenizer + grounding downsamplers (once per sample) --------------------
+ * k x k stride-k patches as GEMM rows, so that Conv2d(k, stride=k) (convnext.py:71-72,79-81: stem 4x4/4, downsample 2x2/2) is a
+ * glg_gemm with the weight packed [Cout, (ky, kx, c)]:  out[(b,oy,ox)][(ky*k+kx)*C + c], bf16, columns [k*k*C, ldo) zero.
+ * _nchw: fp32 NCHW source resampled by nearest onto a virtual Hv x Wv grid first (F.interpolate(x, resize_input),
+ *        hed_grounding_net.py:42 - fused here);  _nhwc: bf16 channels-last source (row stride ldx, C % 8 == 0). */
+int glg_patchify_nchw(const float* x, void* out, int64_t ldo, int32_t B, int32_t C, int32_t Hs, int32_t Ws, int32_t Hv, int32_t Wv,
+                      int32_t k, void* stream);
+int glg_patchify_nhwc(const void* x, int64_t ldx, void* out, int64_t ldo, int32_t B, int32_t H, int32_t Wd, int32_t C, int32_t k, void* stream);
+/* LayerNorm over the first C columns of `rows` strided bf16 rows (the channels_first LayerNorm of convnext.py:119-139 on a
+ * channels-last tensor; two-pass statistics in registers); y columns [C, Cpad) are written as zeros (K padding). In place is fine. */
+int glg_layernorm_rows(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma, const float* beta, int64_t rows,
+                       int32_t C, int32_t Cpad, float eps, void* stream);
+/* ConvNeXt block front (convnext.py:40-43): depthwise 7x7 pad 3 + bias, then LayerNorm over channels, one pass.
+ * x / y NHWC bf16; w fp32 packed [49][C] (tap-major); y columns [C, Cpad) are zeros. */
+int glg_dwconv7_ln(const void* x, int64_t ldx, void* y, int64_t ldy, const float* w, const float* bias, const float* gamma,
+                   const float* beta, int32_t B, int32_t H, int32_t Wd, int32_t C, int32_t Cpad, float eps, void* stream);
+/* Grounding tokens of a spatial map before the PositionNet MLP (hed_grounding_net.py:47-56): for the n tokens of sample b
+ * y[b, t, :] = x[b, t, :] * mask[b] + null_feat * (1 - mask[b]) + pos[t, :]   (x, y bf16 rows; mask [B], null_feat [C], pos [n, C] fp32). */
+int glg_spatial_tokens(const void* x, int64_t ldx, const float* mask, const float* null_feat, const float* pos, void* y, int64_t ldy,
+                       int32_t B, int32_t n, int32_t C, void* stream);
+/* F.interpolate on fp32 NCHW planes: y[B, C, Ho, Wo] from channels 0..C-1 of x (batch stride x_batch_stride elements).
+ * mode 0 = nearest, 1 = bicubic (align_corners=False; hed/canny/depth/normal_grounding_downsampler.py). */
+int glg_resize_plane(const float* x, int64_t x_batch_stride, float* y, int32_t B, int32_t C, int32_t Hs, int32_t Ws, int32_t Ho, int32_t Wo,
+                     int32_t mode, void* stream);
+/* Direct Conv2d with Cout in {3, 4, 8, 16} on fp32 NCHW (the downsamplers' Conv2d(.,.,4,2,1) pairs, sem_grounding_net.py:21
+ * in_conv 3x3): the input is the source resampled by nearest onto a virtual Hv x Wv grid (Hv = Hs, Wv = Ws: as is);
+ * w fp32 packed [Cin*k*k][Cout]; optional SiLU; y [B, Cout, Ho, Wo]. */
+int glg_conv2d_small(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t Cin, int32_t Hs, int32_t Ws, int32_t Hv,
+                     int32_t Wv, int32_t Cout, int32_t k, int32_t stride, int32_t pad, int32_t silu, void* stream);
 
 /* ---- sampler update (plms.py:121-158, ddim.py:113-134), one fused fp32 kernel ---------------
  * e      = e_u + g*(e_c - e_u)                       (if e_uncond != NULL, else e = e_cond)

@@ -1,0 +1,8 @@
+"""Grounding tokeniser container for Canny edge maps (configs/cc3m_canny.yaml); ConvNeXt-tiny + mask / position embedding + MLP run in
+gligen_b200.spatial (glg_patchify_*, glg_dwconv7_ln, glg_gemm, glg_spatial_tokens).
+Reference: ldm/modules/diffusionmodules/canny_grounding_net.py."""
+from ldm.modules.diffusionmodules.grounding_common import make_position_net
+
+
+class PositionNet(make_position_net("canny")):
+    pass

@@ -17,7 +17,8 @@ import torch.nn as nn
 from gligen_b200.spec import UNetConfig, unet_param_shapes
 from ldm.modules.attention import (BasicTransformerBlock, CrossAttention, FeedForward, GatedSelfAttentionDense,
                                    ParamNode, SelfAttention, SpatialTransformer)
-from ldm.modules.diffusionmodules.grounding_common import attach_params, tokenizer_config
+from gligen_b200.spec import SPATIAL_TOKENIZERS
+from ldm.modules.diffusionmodules.grounding_common import attach_params, downsampler_config, tokenizer_config
 from ldm.util import instantiate_from_config
 
 _TOKENIZERS = {
@@ -25,6 +26,8 @@ _TOKENIZERS = {
     "ldm.modules.diffusionmodules.text_image_grounding_net.PositionNet": "text_image",
     "ldm.modules.diffusionmodules.keypoint_grounding_net.PositionNet": "keypoint",
 }
+_TOKENIZERS.update({f"ldm.modules.diffusionmodules.{t}_grounding_net.PositionNet": t for t in SPATIAL_TOKENIZERS})
+_DOWNSAMPLERS = {f"ldm.modules.diffusionmodules.{t}_grounding_downsampler.GroundingDownsampler": t for t in SPATIAL_TOKENIZERS}
 
 
 class TimestepEmbedSequential(ParamNode):
@@ -70,11 +73,14 @@ class UNetModel(ParamNode):
         unsupported = []
         if fuser_type != "gatedSA":
             unsupported.append(f"fuser_type={fuser_type} (every shipped config uses gatedSA)")
-        if grounding_downsampler is not None:
-            unsupported.append("grounding_downsampler (spatial-map modalities are outside the accelerated path)")
+        target = (grounding_tokenizer or {}).get("target")
+        ds_target = (grounding_downsampler or {}).get("target")
+        if grounding_downsampler is not None and (ds_target not in _DOWNSAMPLERS or _DOWNSAMPLERS[ds_target] != _TOKENIZERS.get(target)):
+            unsupported.append(f"grounding_downsampler target {ds_target!r} (must be the downsampler of the tokenizer's modality)")
+        if grounding_downsampler is not None and inpaint_mode:
+            unsupported.append("grounding_downsampler with inpaint_mode (the reference stops at a breakpoint() there, openaimodel.py:445-446)")
         if use_scale_shift_norm or transformer_depth != 1 or dims != 2 or not conv_resample or dropout:
             unsupported.append("use_scale_shift_norm / transformer_depth != 1 / dims != 2 / conv_resample=False / dropout")
-        target = (grounding_tokenizer or {}).get("target")
         if target not in _TOKENIZERS:
             unsupported.append(f"grounding_tokenizer target {target!r}")
         if unsupported:
@@ -106,8 +112,13 @@ class UNetModel(ParamNode):
                           num_heads=num_heads, transformer_depth=transformer_depth, context_dim=context_dim,
                           fuser_type=fuser_type, inpaint_mode=inpaint_mode)
         self.cfg = tokenizer_config(_TOKENIZERS[target], base, **grounding_tokenizer.get("params", {}))
+        if grounding_downsampler is not None:           # openaimodel.py:293-297
+            self.cfg = downsampler_config(_TOKENIZERS[target], self.cfg, **grounding_downsampler.get("params", {}))
+            self.downsample_net = instantiate_from_config(grounding_downsampler)
+            self.additional_channel_from_downsampler = self.downsample_net.out_dim
+            self.first_conv_type = "GLIGEN"
         shapes = unet_param_shapes(self.cfg)
-        body = {k: v for k, v in shapes.items() if not k.startswith("position_net.")}
+        body = {k: v for k, v in shapes.items() if not k.startswith(("position_net.", "downsample_net."))}
         attach_params(self, body, "", _node_class)
         self.position_net = instantiate_from_config(grounding_tokenizer)
         self._fusers = [m for m in self.modules() if type(m) == GatedSelfAttentionDense]
@@ -191,12 +202,22 @@ class UNetModel(ParamNode):
         if getattr(self, "_sd_applied", False) and self.first_conv_type == "SD" and hasattr(self, "GLIGEN_first_conv_state_dict"):
             return                                       # already swapped in: idempotent
         _, w, b = self._sd_conv_cache
-        if tuple(w.shape) != tuple(conv.weight.shape):
+        narrower = self.downsample_net is not None and w.shape[1] == self.in_channels and tuple(w.shape[:1] + w.shape[2:]) == tuple(
+            conv.weight.shape[:1] + conv.weight.shape[2:])
+        if tuple(w.shape) != tuple(conv.weight.shape) and not narrower:
             raise RuntimeError(f"{path}: weight {tuple(w.shape)} does not fit the first conv {tuple(conv.weight.shape)}")
         self.GLIGEN_first_conv_state_dict = deepcopy(conv.state_dict())
         with torch.no_grad():
-            conv.weight.copy_(w)
-            conv.bias.copy_(b)
+            if narrower:
+                # spatial modalities: the reference replaces the (4 + d)-channel conv by SD's 4-channel one and stops feeding the
+                # downsampler planes (first_conv_type == "SD", openaimodel.py:407-411, 441); the engine keeps its plan and gets
+                # zero weights on the extra channels (Engine.set_first_conv)
+                dev = conv.weight.device
+                conv.weight = nn.Parameter(w.to(dev), requires_grad=False)
+                conv.bias = nn.Parameter(b.to(dev), requires_grad=False)
+            else:
+                conv.weight.copy_(w)
+                conv.bias.copy_(b)
         if self._engine is not None and not self._engine_stale:
             self._engine.set_first_conv(conv.weight, conv.bias)
         self.first_conv_type = "SD"
@@ -218,7 +239,8 @@ class UNetModel(ParamNode):
         eng = self.engine()
         self._sync_scales(eng)
         return eng.forward(input["x"], input["timesteps"], input["context"], self._grounding(input),
-                           input.get("inpainting_extra_input") if self.inpaint_mode else None)
+                           input.get("inpainting_extra_input") if self.inpaint_mode else None,
+                           input.get("grounding_extra_input") if self.downsample_net is not None else None)
 
     @torch.no_grad()
     def forward_cfg(self, input, uc):
@@ -226,7 +248,8 @@ class UNetModel(ParamNode):
         eng = self.engine()
         self._sync_scales(eng)
         return eng.forward_cfg(input["x"], input["timesteps"], input["context"], uc, input["grounding_input"],
-                               input.get("inpainting_extra_input") if self.inpaint_mode else None)
+                               input.get("inpainting_extra_input") if self.inpaint_mode else None,
+                               input.get("grounding_extra_input") if self.downsample_net is not None else None)
 
 
 # names this drop-in does not define resolve to the reference module of the same name when a reference checkout

@@ -65,6 +65,37 @@ def mount(prefer: str = "auto") -> str:
     return _mounted
 
 
+def shim_timm() -> None:
+    """The reference's convnext.py imports `timm` (absent here, no network) for three names that never run on this path:
+    `trunc_normal_` (init only, commented out), `DropPath` (drop_path = 0 -> nn.Identity is used) and `register_model` (a
+    registry decorator).  Stand-ins for exactly those names let the UNMODIFIED reference module import.  `convnext_tiny(
+    pretrained=True)` (hed_grounding_net.py:20) downloads ImageNet weights: torch.hub.load_state_dict_from_url is pointed at
+    an empty state dict (strict=False load); the parity runs then load the seeded synthetic weights over every tensor."""
+    import types
+    if "timm" not in sys.modules:
+        timm = types.ModuleType("timm"); models = types.ModuleType("timm.models")
+        layers = types.ModuleType("timm.models.layers"); registry = types.ModuleType("timm.models.registry")
+        layers.trunc_normal_ = lambda t, std=0.02: torch.nn.init.trunc_normal_(t, std=std)
+        layers.DropPath = torch.nn.Identity
+        registry.register_model = lambda fn: fn
+        timm.models, models.layers, models.registry = models, layers, registry
+        sys.modules.update({"timm": timm, "timm.models": models, "timm.models.layers": layers, "timm.models.registry": registry})
+    torch.hub.load_state_dict_from_url = lambda *a, **k: {"model": {}}
+
+
+def spatial_configs(cfg):
+    """(grounding_tokenizer, grounding_downsampler) config dicts of a spatial modality, as configs/cc3m_hed.yaml etc. give them."""
+    t = cfg.tokenizer
+    tok = dict(resize_input=cfg.tok_resize, out_dim=cfg.tok_out_dim)
+    ds = dict(out_dim=cfg.ds_out_dim)
+    if t != "hed":
+        ds["resize_input"] = cfg.ds_resize
+    if t == "sem":
+        tok["in_dim"] = ds["in_dim"] = cfg.sem_in_dim
+    return (dict(target=f"ldm.modules.diffusionmodules.{t}_grounding_net.PositionNet", params=tok),
+            dict(target=f"ldm.modules.diffusionmodules.{t}_grounding_downsampler.GroundingDownsampler", params=ds))
+
+
 def is_reference_module(mod) -> bool:
     f = getattr(sys.modules[mod.__module__], "__file__", "") or ""
     return f.startswith(REF_DIR) or "gligen_reference.zip" in f
@@ -76,6 +107,15 @@ def ref_model(cfg, device="cpu"):
     mount()
     from ldm.modules.diffusionmodules.openaimodel import UNetModel
     assert is_reference_module(UNetModel)
+    if cfg.spatial:
+        shim_timm()
+        tokc, dsc = spatial_configs(cfg)
+        m = UNetModel(image_size=cfg.image_size, in_channels=cfg.in_channels, out_channels=cfg.out_channels,
+                      model_channels=cfg.model_channels, attention_resolutions=list(cfg.attention_resolutions),
+                      num_res_blocks=cfg.num_res_blocks, channel_mult=list(cfg.channel_mult), num_heads=cfg.num_heads,
+                      transformer_depth=1, context_dim=cfg.context_dim, fuser_type="gatedSA", use_checkpoint=True,
+                      inpaint_mode=cfg.inpaint_mode, grounding_tokenizer=tokc, grounding_downsampler=dsc)
+        return m.to(device).eval()
     tok = {
         "text": ("ldm.modules.diffusionmodules.text_grounding_net.PositionNet", dict(in_dim=cfg.tok_in_dim, out_dim=cfg.tok_out_dim)),
         "text_image": ("ldm.modules.diffusionmodules.text_image_grounding_net.PositionNet", dict(in_dim=cfg.tok_in_dim, out_dim=cfg.tok_out_dim)),
@@ -92,6 +132,8 @@ def ref_model(cfg, device="cpu"):
 def ref_grounding_input(cfg):
     mount()
     import importlib
+    if cfg.spatial:
+        return importlib.import_module(f"grounding_input.{cfg.tokenizer}_grounding_tokinzer_input").GroundingNetInput()
     name = {"text": "text_grounding_tokinzer_input", "text_image": "text_image_grounding_tokinzer_input",
             "keypoint": "keypoint_grounding_tokinzer_input"}[cfg.tokenizer]
     return importlib.import_module(f"grounding_input.{name}").GroundingNetInput()
@@ -162,7 +204,7 @@ def run_reference_sampler(cfg, sd: Dict[str, torch.Tensor], inp: Dict[str, objec
     sampler = cls(diffusion, model, alpha_generator_func=partial(SO.alpha_generator, type=alpha_type), set_alpha_scale=set_alpha_scale)
     B = inp["x"].shape[0]
     input = dict(x=inp["x"].clone().to(device), timesteps=None, context=inp["context"].to(device), grounding_input=grounding,
-                 inpainting_extra_input=extra, grounding_extra_input=None)
+                 inpainting_extra_input=extra, grounding_extra_input=_to(inp.get("grounding_extra_input"), device))
     shape = (B, cfg.in_channels, cfg.image_size, cfg.image_size)
     cwd = os.getcwd()
     os.chdir(_mounted)                                         # SD_input_conv_weight_bias.pth is read CWD-relative

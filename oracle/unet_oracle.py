@@ -58,6 +58,9 @@ def position_net(cfg: UNetConfig, sd: Dict[str, torch.Tensor], g: Dict[str, torc
     keypoint:    keypoint_grounding_net.py:34-58
     """
     pn = "position_net"
+    if cfg.spatial:
+        from oracle.spatial_oracle import position_net_spatial
+        return position_net_spatial(cfg, sd, g)
     if cfg.tokenizer == "text":
         m = g["masks"].unsqueeze(-1)
         xyxy = fourier_embed(g["boxes"], cfg.fourier_freqs)
@@ -184,7 +187,7 @@ def res_block(sd, p, x, emb):
 def unet_forward(cfg: UNetConfig, sd: Dict[str, torch.Tensor], x: torch.Tensor, timesteps: torch.Tensor,
                  context: torch.Tensor, grounding: Dict[str, torch.Tensor], scale: float = 1.0,
                  inpainting_extra_input: Optional[torch.Tensor] = None,
-                 taps: Optional[dict] = None) -> torch.Tensor:
+                 taps: Optional[dict] = None, grounding_extra_input: Optional[torch.Tensor] = None) -> torch.Tensor:
     """openaimodel.py:420-464 UNetModel.forward.  `scale` is GatedSelfAttentionDense.scale
     (gligen_inference.py:24-28).  `taps`, if given, receives named intermediate activations."""
     objs = position_net(cfg, sd, grounding)
@@ -192,6 +195,14 @@ def unet_forward(cfg: UNetConfig, sd: Dict[str, torch.Tensor], x: torch.Tensor, 
     emb = F.linear(emb, sd["time_embed.0.weight"], sd["time_embed.0.bias"])
     emb = F.linear(F.silu(emb), sd["time_embed.2.weight"], sd["time_embed.2.bias"])
     h = x.float()
+    if cfg.ds_out_dim and grounding_extra_input is not None:
+        # openaimodel.py:441-443: downsample_net output joins the latent while first_conv_type == "GLIGEN"; pass
+        # grounding_extra_input=None to state the "SD" first-conv case (after restore_first_conv_from_SD)
+        from oracle.spatial_oracle import grounding_downsampler
+        temp = grounding_downsampler(cfg, sd, grounding_extra_input, cfg.image_size)
+        if taps is not None:
+            taps["downsample_net"] = temp
+        h = torch.cat([h, temp], dim=1)
     if cfg.inpaint_mode:
         h = torch.cat([h, inpainting_extra_input], dim=1)
     if taps is not None:

@@ -64,6 +64,10 @@ class RefOps:
                 v = v + rowbias.float()[idx]
             if act == 1:
                 v = F.silu(v)
+            elif act == 2:
+                v = F.gelu(v)
+            elif act == 3:
+                v = v * torch.sigmoid(1.702 * v)
             if gate is not None:
                 v = v * gate.float()
             if residual is not None:
@@ -85,6 +89,53 @@ class RefOps:
         sim = torch.einsum("bhic,bhjc->bhij", qf, kf) * (d_head ** -0.5)
         o = torch.einsum("bhij,bhjc->bhic", sim.softmax(dim=-1), vf)
         out.copy_(o.permute(0, 2, 1, 3).reshape(B, Lq, heads * d_head).to(out.dtype))
+
+    # -- spatial grounding modalities ----------------------------------------------------------------------------
+    def patchify_nchw(self, x, out, Hv, Wv, k):
+        self.launches += 1
+        B, C = x.shape[:2]
+        xv = F.interpolate(x.float(), (Hv, Wv))
+        p = xv.view(B, C, Hv // k, k, Wv // k, k).permute(0, 2, 4, 3, 5, 1).reshape(-1, k * k * C)       # (b, oy, ox), (ky, kx, c)
+        out.zero_()
+        out[:, : k * k * C] = p.to(out.dtype)
+
+    def patchify_nhwc(self, x, out, H, W, C, k):
+        self.launches += 1
+        xv = x.reshape(-1, H, W, x.shape[-1])[..., :C]
+        B = xv.shape[0]
+        out.copy_(xv.reshape(B, H // k, k, W // k, k, C).permute(0, 1, 3, 2, 4, 5).reshape(-1, k * k * C))
+
+    def layernorm_rows(self, x, y, gamma, beta, C, eps):
+        self.launches += 1
+        v = F.layer_norm(x[..., :C].float(), (C,), gamma.float(), beta.float(), eps)
+        y.zero_()
+        y[..., :C] = v.to(y.dtype)
+
+    def dwconv7_ln(self, x, y, w, bias, gamma, beta, B, H, W, C, eps):
+        self.launches += 1
+        xv = x.reshape(B, H, W, -1)[..., :C].permute(0, 3, 1, 2).float()
+        h = F.conv2d(xv, w.float().t().reshape(C, 1, 7, 7), bias.float(), padding=3, groups=C).permute(0, 2, 3, 1)
+        v = F.layer_norm(h, (C,), gamma.float(), beta.float(), eps).reshape(B * H * W, C)
+        y.zero_()
+        y.reshape(B * H * W, -1)[:, :C] = v.to(y.dtype)
+
+    def spatial_tokens(self, x, mask, null_feat, pos, y, n):
+        self.launches += 1
+        C = x.shape[-1]
+        xv = x.reshape(-1, n, C).float()
+        m = mask.float().view(-1, 1, 1)
+        y.copy_((xv * m + null_feat.float().view(1, 1, -1) * (1 - m) + pos.float().view(1, n, C)).reshape(y.shape).to(y.dtype))
+
+    def resize_plane(self, x, y, C, mode):
+        self.launches += 1
+        y.copy_(F.interpolate(x[:, :C].float(), tuple(y.shape[2:]), mode=mode))
+
+    def conv2d_small(self, x, w, bias, y, k, stride, pad, silu, virtual=None):
+        self.launches += 1
+        Cin, Cout = x.shape[1], y.shape[1]
+        xv = x.float() if virtual is None else F.interpolate(x.float(), tuple(virtual))
+        v = F.conv2d(xv, w.float().reshape(Cin, k, k, Cout).permute(3, 0, 1, 2), bias.float(), stride=stride, padding=pad)
+        y.copy_(F.silu(v) if silu else v)
 
     def softmax_rows(self, s, p, scale):
         self.launches += 1

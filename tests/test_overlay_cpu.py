@@ -37,8 +37,12 @@ SCRIPT = textwrap.dedent('''
     from ldm.modules.diffusionmodules.util import checkpoint, conv_nd, zero_module
     from ldm.util import log_txt_as_img
     assert "_gligen_b200_shadowed" in GEGLU.__module__ and "_gligen_b200_shadowed" in conv_nd.__module__
-    import grounding_input.hed_grounding_tokinzer_input as H
-    assert H.__file__.startswith(%(ref)r)
+    import grounding_input.hed_grounding_tokinzer_input as H            # spatial modalities are drop-ins too since round 2
+    assert H.__file__.startswith(%(repo)r)
+    import ldm.modules.diffusionmodules.hed_grounding_net as HN, ldm.modules.diffusionmodules.sem_grounding_downsampler as SD
+    assert HN.__file__.startswith(%(repo)r) and SD.__file__.startswith(%(repo)r)
+    import ldm.modules.diffusionmodules.grounding_net_example as EX       # a reference-only module next to them still resolves
+    assert EX.__file__.startswith(%(ref)r)
     # the reference VAE decoder actually runs in this overlay (tiny config)
     import torch
     dd = dict(double_z=True, z_channels=4, resolution=32, in_channels=3, out_ch=3, ch=32, ch_mult=[1, 2], num_res_blocks=1,
