@@ -316,6 +316,10 @@ extern "C" int glg_attention(const GlgAttnArgs* a, void* stream) {
   if ((a->q_row | a->k_row | a->v_row | a->q_batch | a->k_batch | a->v_batch) % 8) return set_error("glg_attention: q/k/v strides must be multiples of 8 elements");
   if ((a->o_row | a->o_batch) % 2) return set_error("glg_attention: output strides must be even");
   if (((uintptr_t)a->q | (uintptr_t)a->k | (uintptr_t)a->v) & 15) return set_error("glg_attention: q/k/v must be 16-byte aligned");
+  if (a->causal) {                    // causal mask: only the short-key kernel implements it (the 77-token CLIP text encoder)
+    const int rc = a->Lk <= 128 ? attention_short_tc(a, reinterpret_cast<cudaStream_t>(stream)) : 1;
+    return rc <= 0 ? rc : set_error("glg_attention: causal attention needs Lk <= 128, d_head % 8 == 0 and 16-byte aligned output rows");
+  }
   if ((g_attn_mode == 0 && a->Lk <= 128) || g_attn_mode == 3) {     // short key sets (the 77-token text context)
     const int rc = attention_short_tc(a, reinterpret_cast<cudaStream_t>(stream));
     if (rc <= 0) return rc;

@@ -29,6 +29,7 @@ namespace glg {
 struct AttnShortParams {
   bf16* o; long long o_row, o_batch;
   int heads, d, Lq, Lk, nkp;          // nkp = Lk rounded up to a multiple of 16
+  int causal;                         // query row r sees keys [0, r] only (the CLIP text encoder's causal mask)
   int tiles_per_cta, n_qtiles;
   int s_cols;                         // TMEM columns reserved for S in each buffer (= nkp)
   int tmem_cols;                      // allocation: 256 or 512
@@ -173,6 +174,8 @@ attn_short_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint32_t par = (uint32_t)((i >> 1) & 1);
       mbar_wait(s_full(g), par);
       tc_fence_after();
+      // keys this row may see: all Lk, or - causal - the first (row + 1)
+      const int lim = p.causal ? min(p.Lk, (t0 + i) * BM + rloc + 1) : p.Lk;
       // pass 1: row maximum (scores are re-read from TMEM in pass 2: 80-128 live registers would cost the 2nd CTA/SM)
       float mx = -INFINITY;
       for (int c = 0; c < nch; ++c) {
@@ -181,7 +184,7 @@ attn_short_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (c * 16 + j < p.Lk) mx = fmaxf(mx, __uint_as_float(sv[j]));
+          if (c * 16 + j < lim) mx = fmaxf(mx, __uint_as_float(sv[j]));
       }
       const float ms = mx * sl2;
       float l = 0.f;
@@ -194,8 +197,8 @@ attn_short_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int j = 0; j < 8; ++j) {
           float a0 = ex2_approx_s(fmaf(__uint_as_float(sv[2 * j]), sl2, -ms));
           float a1 = ex2_approx_s(fmaf(__uint_as_float(sv[2 * j + 1]), sl2, -ms));
-          if (c * 16 + 2 * j >= p.Lk) a0 = 0.f;                 // padding keys (K rows zero-filled by TMA)
-          if (c * 16 + 2 * j + 1 >= p.Lk) a1 = 0.f;
+          if (c * 16 + 2 * j >= lim) a0 = 0.f;                  // padding keys (K rows zero-filled by TMA) / masked keys
+          if (c * 16 + 2 * j + 1 >= lim) a1 = 0.f;
           l += a0 + a1;
           pk[j] = pack_bf16x2(a0, a1);
         }
@@ -283,6 +286,7 @@ int attention_short_tc(const GlgAttnArgs* a, cudaStream_t st) {
   p.o = (bf16*)a->out; p.o_row = a->o_row; p.o_batch = a->o_batch;
   p.heads = a->heads; p.d = a->d_head; p.Lq = a->Lq; p.Lk = a->Lk;
   p.nkp = (a->Lk + 15) / 16 * 16;
+  p.causal = a->causal;
   p.n_qtiles = (a->Lq + ast::BM - 1) / ast::BM;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.tiles_per_cta = 1; p.s_cols = 0;

@@ -75,7 +75,11 @@ __device__ __forceinline__ float ex2_poly3(float x) {
 // POLY: of every 8 score pairs, the last POLY pairs take their exp2 from ex2_poly3 instead of the MUFU
 // KO (timing experiments only, results are wrong): 1 no exp2 (plain FMA instead), 2 K / V tiles loaded only for the first ring
 // pass, 4 no P.V MMAs, 8 no QK^T MMAs, 16 no TMEM score loads, 32 no P store, 64 clock probes of CTA (0,0,0)
-template <int DPAD, int POLY = 0, int KO = 0>      // head dim rounded up to a multiple of 16 with one spare column for the row sums: d_head < DPAD <= 64
+// VAR (measured variants of the per-tile chains, profiles/r2_attention_l0.md; 4 = the issuer warps' waits by lane 0 only):
+//   1  mbarrier waits by lane 0 only + __syncwarp (32 lanes polling the same mbarrier serialise in the shared-memory pipe)
+//   2  the exponentials of the whole tile are computed BEFORE the wait for P.V of the previous tile (only the P stores and the rare
+//      O rescale need it), taking that wait off the per-tile critical path
+template <int DPAD, int POLY = 0, int KO = 0, int VAR = 0>      // head dim rounded up to a multiple of 16 with one spare column for the row sums: d_head < DPAD <= 64
 __global__ void __launch_bounds__(atc3::THREADS, 1)
 attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnTc3Params p) {
@@ -184,9 +188,17 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, DPAD, true);    // B (V) is MN-major
       const bool leader = elect_one();
       const uint32_t sQg = sQ + g * Q_BYTES;
+      auto mbar_wait_i = [&](uint32_t bar, uint32_t parity) {      // VAR & 4: the issuer warps' waits by lane 0 only
+        if (VAR & 4) {
+          if (lane == 0) mbar_wait(bar, parity);
+          __syncwarp();
+        } else {
+          mbar_wait(bar, parity);
+        }
+      };
       auto issue_qk = [&](int j) {
         const int stage = j % STAGES;
-        mbar_wait(kv_full(stage), (uint32_t)((j / STAGES) & 1));
+        mbar_wait_i(kv_full(stage), (uint32_t)((j / STAGES) & 1));
         tc_fence_after();
         if (leader) {
           const uint32_t sk = sKV + stage * 2 * KV_BYTES;
@@ -202,14 +214,14 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       issue_qk(0);
       for (int j = 0; j < nkt; ++j) {
         if (j + 1 < nkt) {
-          mbar_wait(s_free(g), (uint32_t)(j & 1));        // S_g of tile j is in registers
+          mbar_wait_i(s_free(g), (uint32_t)(j & 1));      // S_g of tile j is in registers
           TC3_STAMP(0);
           issue_qk(j + 1);
           TC3_STAMP(1);
         }
         const int stage = j % STAGES;
-        mbar_wait(kv_ready(stage), (uint32_t)((j / STAGES) & 1));
-        mbar_wait(p_full(g), (uint32_t)(j & 1));
+        mbar_wait_i(kv_ready(stage), (uint32_t)((j / STAGES) & 1));
+        mbar_wait_i(p_full(g), (uint32_t)(j & 1));
         tc_fence_after();
         TC3_STAMP(2);
         if (leader) {
@@ -241,8 +253,16 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const long long t_end = clock64() + (long long)g * p.stagger;
       while (clock64() < t_end) {}
     }
+    auto wait_bar = [&](uint32_t bar, uint32_t parity) {
+      if (VAR & 1) {
+        if (lane == 0) mbar_wait(bar, parity);
+        __syncwarp();
+      } else {
+        mbar_wait(bar, parity);
+      }
+    };
     for (int j = 0, it = 0; j < (g < nact ? nkt : 0); ++j, ++it) {
-      mbar_wait(s_full(g), (uint32_t)(it & 1));
+      wait_bar(s_full(g), (uint32_t)(it & 1));
       tc_fence_after();
       TC3_STAMP(0);
       const int valid = p.Lk - j * BN;           // < 64 only in the last tile: keys [valid, 64) are padding
@@ -275,14 +295,19 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mx1 = fmaxf(mx1, fmaxf(__uint_as_float(SC(i + 2)), __uint_as_float(SC(i + 3))));
       }
       const float m_new = fmaxf(m_ref, fmaxf(mx0, mx1));
+      bool waited = false;
       if (it == 0) {
         m_ref = m_new;
       } else {
-        // P.V of this warpgroup's previous tile must be done before P_g is overwritten and before O_g is rescaled
-        mbar_wait(p_free(g), (uint32_t)((it - 1) & 1));
-        tc_fence_after();
         const bool need = (m_new - m_ref) * sl2 > RESCALE_THRESHOLD;
-        if (__any_sync(0xffffffffu, need)) {     // tcgen05.ld / st are warp-collective: the whole warp rescales its rows
+        const bool any_need = __any_sync(0xffffffffu, need);     // tcgen05.ld / st are warp-collective: the whole warp rescales its rows
+        if (!(VAR & 2) || any_need) {
+          // P.V of this warpgroup's previous tile must be done before P_g is overwritten and before O_g is rescaled
+          wait_bar(p_free(g), (uint32_t)((it - 1) & 1));
+          tc_fence_after();
+          waited = true;
+        }
+        if (any_need) {
           const float f = need ? ex2_approx3((m_ref - m_new) * sl2) : 1.0f;
           if (need) m_ref = m_new;
           // rare path, 4 columns at a time: the 64 scores stay live across it
@@ -301,6 +326,25 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       TC3_STAMP(2);
       // P = exp2((S - m_ref) * scale) -> bf16 in P_g
       const float ms = m_ref * sl2;
+      if (VAR & 2) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float x0 = fmaf(__uint_as_float(SC(2 * i)), sl2, -ms), x1 = fmaf(__uint_as_float(SC(2 * i + 1)), sl2, -ms);
+          const float a0 = (KO & 1) ? x0 * 0.001f : ((i & 7) >= 8 - POLY) ? ex2_poly3(x0) : ex2_approx3(x0);
+          const float a1 = (KO & 1) ? x1 * 0.001f : ((i & 7) >= 8 - POLY) ? ex2_poly3(x1) : ex2_approx3(x1);
+          pk[i] = pack_bf16x2(a0, a1);
+        }
+        if (it > 0 && !waited) {
+          wait_bar(p_free(g), (uint32_t)((it - 1) & 1));
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                       ::"r"(p_addr + k * 8), "r"(pk[8 * k]), "r"(pk[8 * k + 1]), "r"(pk[8 * k + 2]), "r"(pk[8 * k + 3]), "r"(pk[8 * k + 4]), "r"(pk[8 * k + 5]),
+                         "r"(pk[8 * k + 6]), "r"(pk[8 * k + 7]) : "memory");
+      } else {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         uint32_t pk[8];
@@ -314,6 +358,7 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (KO & 32) { if (pk[0] + pk[1] + pk[2] + pk[3] + pk[4] + pk[5] + pk[6] + pk[7] == 0x12345u) m_ref += 1.f; }
         else asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                      ::"r"(p_addr + k * 8), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+      }
       }
       TC3_STAMP(3);
       tmem_st_wait();
@@ -373,10 +418,12 @@ extern int g_attn_tc2_poly;      // attention_tc2.cu: GLG_ATTN_POLY / glg_debug_
 int g_attn_tc3_ko = 0;
 int g_attn_tc3_stagger = -1;     // -1: GLG_ATTN_STAGGER env (default 0)
 
-template <int DPAD, int POLY, int KO = 0>
+int g_attn_tc3_var = -1;         // -1: GLG_ATTN_TC3_VAR env (default below)
+
+template <int DPAD, int POLY, int KO = 0, int VAR = 0>
 static int launch_attn_tc3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTc3Params& p, int B, cudaStream_t st) {
   static bool attr_set = false;
-  auto kern = attn_tc3_kernel<DPAD, POLY, KO>;
+  auto kern = attn_tc3_kernel<DPAD, POLY, KO, VAR>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, atc3::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(std::string("cudaFuncSetAttribute(attn_tc3): ") + cudaGetErrorString(e));
@@ -422,13 +469,23 @@ int attention_tc3(const GlgAttnArgs* a, cudaStream_t st) {
   // setter override it; the two-warpgroup kernel keeps its own default (0).
   int poly = g_attn_tc2_poly;
   if (poly < 0) { const char* e = getenv("GLG_ATTN_POLY"); poly = e ? atoi(e) : 2; }
+  if (g_attn_tc3_var < 0) { const char* e = getenv("GLG_ATTN_TC3_VAR"); g_attn_tc3_var = e ? atoi(e) : 0; }
+  const int var = g_attn_tc3_var;
   switch (dpad) {
     case 16: return launch_attn_tc3<16, 0>(tq, tk, tv, p, a->B, st);
     case 32: return launch_attn_tc3<32, 0>(tq, tk, tv, p, a->B, st);
     case 48:
       switch (poly) {
         case 1: return launch_attn_tc3<48, 1>(tq, tk, tv, p, a->B, st);
-        case 2: return launch_attn_tc3<48, 2>(tq, tk, tv, p, a->B, st);
+        case 2:
+          switch (var) {
+            case 1: return launch_attn_tc3<48, 2, 0, 1>(tq, tk, tv, p, a->B, st);
+            case 2: return launch_attn_tc3<48, 2, 0, 2>(tq, tk, tv, p, a->B, st);
+            case 3: return launch_attn_tc3<48, 2, 0, 3>(tq, tk, tv, p, a->B, st);
+            case 5: return launch_attn_tc3<48, 2, 0, 5>(tq, tk, tv, p, a->B, st);
+            case 7: return launch_attn_tc3<48, 2, 0, 7>(tq, tk, tv, p, a->B, st);
+            default: return launch_attn_tc3<48, 2>(tq, tk, tv, p, a->B, st);
+          }
         case 3: return launch_attn_tc3<48, 3>(tq, tk, tv, p, a->B, st);
         case 4: return launch_attn_tc3<48, 4>(tq, tk, tv, p, a->B, st);
         default:
@@ -455,3 +512,4 @@ int attention_tc3(const GlgAttnArgs* a, cudaStream_t st) {
 
 extern "C" void glg_debug_attn_tc3_knockout(int ko) { glg::g_attn_tc3_ko = ko; }
 extern "C" void glg_debug_attn_tc3_stagger(int clocks) { glg::g_attn_tc3_stagger = clocks; }
+extern "C" void glg_debug_attn_tc3_variant(int var) { glg::g_attn_tc3_var = var; }

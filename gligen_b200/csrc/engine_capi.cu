@@ -100,6 +100,23 @@ int dispatch(const EOp& op, void* st) {
   if (n == "glg_cast_f32_bf16") return glg_cast_f32_bf16((const float*)A_P(0), A_P(1), A_I(2), st);
   if (n == "glg_softmax_rows") return glg_softmax_rows((const float*)A_P(0), A_I(1), A_P(2), A_I(3), A_I(4), A_I32(5), A_F(6), st);
   if (n == "glg_copy_rows") return glg_copy_rows(A_P(0), A_I(1), A_P(2), A_I(3), A_I(4), A_I32(5), st);
+  // spatial grounding modalities: ConvNeXt tokenizer + grounding downsampler steps (static part of the plan)
+  if (n == "glg_patchify_nchw")
+    return glg_patchify_nchw((const float*)A_P(0), A_P(1), A_I(2), A_I32(3), A_I32(4), A_I32(5), A_I32(6), A_I32(7), A_I32(8), A_I32(9), st);
+  if (n == "glg_patchify_nhwc") return glg_patchify_nhwc(A_P(0), A_I(1), A_P(2), A_I(3), A_I32(4), A_I32(5), A_I32(6), A_I32(7), A_I32(8), st);
+  if (n == "glg_layernorm_rows")
+    return glg_layernorm_rows(A_P(0), A_I(1), A_P(2), A_I(3), (const float*)A_P(4), (const float*)A_P(5), A_I(6), A_I32(7), A_I32(8), A_F(9), st);
+  if (n == "glg_dwconv7_ln")
+    return glg_dwconv7_ln(A_P(0), A_I(1), A_P(2), A_I(3), (const float*)A_P(4), (const float*)A_P(5), (const float*)A_P(6), (const float*)A_P(7),
+                          A_I32(8), A_I32(9), A_I32(10), A_I32(11), A_I32(12), A_F(13), st);
+  if (n == "glg_spatial_tokens")
+    return glg_spatial_tokens(A_P(0), A_I(1), (const float*)A_P(2), (const float*)A_P(3), (const float*)A_P(4), A_P(5), A_I(6), A_I32(7), A_I32(8),
+                              A_I32(9), st);
+  if (n == "glg_resize_plane")
+    return glg_resize_plane((const float*)A_P(0), A_I(1), (float*)A_P(2), A_I32(3), A_I32(4), A_I32(5), A_I32(6), A_I32(7), A_I32(8), A_I32(9), st);
+  if (n == "glg_conv2d_small")
+    return glg_conv2d_small((const float*)A_P(0), (const float*)A_P(1), (const float*)A_P(2), (float*)A_P(3), A_I32(4), A_I32(5), A_I32(6), A_I32(7),
+                            A_I32(8), A_I32(9), A_I32(10), A_I32(11), A_I32(12), A_I32(13), A_I32(14), st);
   return set_error("glg_engine_run: unknown op '" + n + "' in the plan");
 }
 }  // namespace

@@ -74,7 +74,8 @@ __global__ void patchify_nhwc_kernel(const bf16* __restrict__ x, long long ldx, 
 // ---- LayerNorm over the first C columns of strided bf16 rows; one warp per row; columns [C, Cpad) of y are zeroed -----------
 // (two-pass in registers: mean, then mean of squared deviations - the reference's channels_first form, convnext.py:135-139)
 constexpr int LNR_MAX_CHUNKS = 4;          // C <= 32 * 8 * 4 = 1024
-__global__ void __launch_bounds__(256) layernorm_rows_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
+template <bool F32OUT>                     // F32OUT: y is fp32 (the text encoder's last_hidden_state), no padding columns
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const bf16* __restrict__ x, long long ldx, void* __restrict__ yv, long long ldy,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              long long rows, int C, int Cpad, float eps) {
   pdl_trigger();
@@ -120,11 +121,17 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const bf16* __restr
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, __ldg(gamma + c8 * 8 + j), __ldg(beta + c8 * 8 + j));
-      uint4 u;
-      u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]); u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
-      *reinterpret_cast<uint4*>(y + row * ldy + c8 * 8) = u;
-    } else if (c8 * 8 < Cpad) {
-      *reinterpret_cast<uint4*>(y + row * ldy + c8 * 8) = make_uint4(0u, 0u, 0u, 0u);
+      if (F32OUT) {
+        float* y = reinterpret_cast<float*>(yv) + row * ldy + c8 * 8;
+        *reinterpret_cast<float4*>(y) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(y + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      } else {
+        uint4 u;
+        u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]); u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(yv) + row * ldy + c8 * 8) = u;
+      }
+    } else if (!F32OUT && c8 * 8 < Cpad) {
+      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(yv) + row * ldy + c8 * 8) = make_uint4(0u, 0u, 0u, 0u);
     }
   }
 }
@@ -306,6 +313,30 @@ __global__ void spatial_tokens_kernel(const bf16* __restrict__ x, long long ldx,
   }
 }
 
+// ---- text-encoder input rows (transformers CLIPTextEmbeddings): out[b, l, :] = bf16(table[ids[b, l], :] + pos[l, :]) ---------------
+// ids outside [0, vocab) are clamped (a corrupt id must not read out of bounds).
+__global__ void embed_tokens_kernel(const int64_t* __restrict__ ids, const float* __restrict__ table, long long vocab, const float* __restrict__ pos,
+                                    bf16* __restrict__ out, long long ldo, int B, int L, int C) {
+  pdl_trigger();
+  pdl_wait();
+  const int c8n = C >> 3;
+  const long long total = (long long)B * L * c8n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % c8n);
+    const long long row = i / c8n;
+    const int l = (int)(row % L);
+    long long id = ids[row];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    const float4* t = reinterpret_cast<const float4*>(table + id * C + c8 * 8);
+    const float4* p = reinterpret_cast<const float4*>(pos + (long long)l * C + c8 * 8);
+    const float4 t0 = __ldg(t), t1 = __ldg(t + 1), p0 = __ldg(p), p1 = __ldg(p + 1);
+    uint4 o;
+    o.x = pack_bf16x2(t0.x + p0.x, t0.y + p0.y); o.y = pack_bf16x2(t0.z + p0.z, t0.w + p0.w);
+    o.z = pack_bf16x2(t1.x + p1.x, t1.y + p1.y); o.w = pack_bf16x2(t1.z + p1.z, t1.w + p1.w);
+    *reinterpret_cast<uint4*>(out + row * ldo + c8 * 8) = o;
+  }
+}
+
 }  // namespace glg
 
 using namespace glg;
@@ -348,10 +379,31 @@ extern "C" int glg_layernorm_rows(const void* x, int64_t ldx, void* y, int64_t l
     return set_error("glg_layernorm_rows: C, Cpad must be multiples of 8 with C <= Cpad <= 1024");
   if (ldx % 8 || ldy % 8 || (((uintptr_t)x | (uintptr_t)y) & 15)) return set_error("glg_layernorm_rows: leading dims must be multiples of 8, pointers 16-byte aligned");
   if (rows <= 0) return 0;
-  launch_k(layernorm_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, ST, 1, (const bf16*)x, (long long)ldx, (bf16*)y, (long long)ldy, gamma, beta,
+  launch_k(layernorm_rows_kernel<false>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, ST, 1, (const bf16*)x, (long long)ldx, y, (long long)ldy, gamma, beta,
            (long long)rows, C, Cpad, eps);
   count_launch();
   return check_launch("layernorm_rows launch");
+}
+
+extern "C" int glg_layernorm_rows_f32(const void* x, int64_t ldx, float* y, int64_t ldy, const float* gamma, const float* beta, int64_t rows,
+                                      int32_t C, float eps, void* stream) {
+  if (C <= 0 || C % 8 || C > 256 * LNR_MAX_CHUNKS) return set_error("glg_layernorm_rows_f32: C must be a multiple of 8, <= 1024");
+  if (ldx % 8 || ldy % 4 || ((uintptr_t)x & 15) || ((uintptr_t)y & 15)) return set_error("glg_layernorm_rows_f32: ldx % 8, ldy % 4, 16-byte aligned pointers");
+  if (rows <= 0) return 0;
+  launch_k(layernorm_rows_kernel<true>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, ST, 1, (const bf16*)x, (long long)ldx, (void*)y, (long long)ldy, gamma, beta,
+           (long long)rows, C, C, eps);
+  count_launch();
+  return check_launch("layernorm_rows_f32 launch");
+}
+
+extern "C" int glg_embed_tokens(const int64_t* ids, const float* table, int64_t vocab, const float* pos, void* out, int64_t ldo, int32_t B, int32_t L,
+                                int32_t C, void* stream) {
+  if (C % 8 || ldo % 8 || ((uintptr_t)out & 15) || (((uintptr_t)table | (uintptr_t)pos) & 15)) return set_error("glg_embed_tokens: C, ldo must be multiples of 8, pointers 16-byte aligned");
+  const long long total = (long long)B * L * (C / 8);
+  if (total <= 0) return 0;
+  launch_k(embed_tokens_kernel, dim3(fe_blocks(total, 256)), dim3(256), 0, ST, 1, ids, table, (long long)vocab, pos, (bf16*)out, (long long)ldo, B, L, C);
+  count_launch();
+  return check_launch("embed_tokens launch");
 }
 
 extern "C" int glg_dwconv7_ln(const void* x, int64_t ldx, void* y, int64_t ldy, const float* w, const float* bias, const float* gamma,

@@ -35,7 +35,7 @@ class GlgAttnArgs(C.Structure):
         ("q_row", c_int64), ("k_row", c_int64), ("v_row", c_int64), ("o_row", c_int64),
         ("q_batch", c_int64), ("k_batch", c_int64), ("v_batch", c_int64), ("o_batch", c_int64),
         ("B", c_int), ("heads", c_int), ("d_head", c_int), ("Lq", c_int), ("Lk", c_int),
-        ("scale", c_float),
+        ("scale", c_float), ("causal", c_int),
     ]
 
 
@@ -64,6 +64,8 @@ SIGNATURES = {
     "glg_patchify_nchw": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "glg_patchify_nhwc": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "glg_layernorm_rows": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_void_p]),
+    "glg_layernorm_rows_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p]),
+    "glg_embed_tokens": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "glg_dwconv7_ln": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "glg_spatial_tokens": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "glg_resize_plane": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
@@ -79,7 +81,7 @@ SIGNATURES = {
                                    c_float, c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 # not part of the public header: test hook
-_DEBUG_SIGNATURES = {"glg_debug_force_bn": (None, [c_int]), "glg_debug_pick_tile": (None, [c_int, c_int, c_int, c_int, c_int, c_int, c_int64, C.POINTER(c_int)]), "glg_debug_attn_mode": (None, [c_int]), "glg_debug_attn_poly": (None, [c_int]), "glg_debug_attn_probe": (None, [c_void_p]), "glg_debug_attn_tc_variant": (None, [c_int]), "glg_debug_gemm_cta2": (None, [c_int]), "glg_debug_splitk": (None, [c_int]), "glg_debug_gemm_bres": (None, [c_int]), "glg_debug_gemm_epi": (None, [c_int]), "glg_debug_gemm_knockout": (None, [c_int]), "glg_debug_attn_poly_share": (None, [c_int]), "glg_debug_attn_tc3_knockout": (None, [c_int]), "glg_debug_attn_tc3_stagger": (None, [c_int])}
+_DEBUG_SIGNATURES = {"glg_debug_force_bn": (None, [c_int]), "glg_debug_pick_tile": (None, [c_int, c_int, c_int, c_int, c_int, c_int, c_int64, C.POINTER(c_int)]), "glg_debug_attn_mode": (None, [c_int]), "glg_debug_attn_poly": (None, [c_int]), "glg_debug_attn_probe": (None, [c_void_p]), "glg_debug_attn_tc_variant": (None, [c_int]), "glg_debug_gemm_cta2": (None, [c_int]), "glg_debug_splitk": (None, [c_int]), "glg_debug_gemm_bres": (None, [c_int]), "glg_debug_gemm_epi": (None, [c_int]), "glg_debug_gemm_knockout": (None, [c_int]), "glg_debug_attn_poly_share": (None, [c_int]), "glg_debug_attn_tc3_knockout": (None, [c_int]), "glg_debug_attn_tc3_stagger": (None, [c_int]), "glg_debug_attn_tc3_variant": (None, [c_int])}
 
 _lib: Optional[C.CDLL] = None
 
@@ -103,7 +105,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.glg_abi_version() != 3:
+    if lib.glg_abi_version() != 4:
         raise GligenLibraryError(f"ABI mismatch: library reports {lib.glg_abi_version()}")
     _lib = lib
     return lib

@@ -133,7 +133,7 @@ class CudaOps:
                    2.0 * (M * K + N * K * taps + M * No) + (2.0 * M * No if residual is not None else 0.0))
 
     # -- attention ---------------------------------------------------------------------------------
-    def attention(self, q, k, v, out, heads: int, d_head: int):
+    def attention(self, q, k, v, out, heads: int, d_head: int, causal: bool = False):
         """q [B, Lq, heads*d] / k, v [B, Lk, heads*d] strided views; out [B, Lq, heads*d]."""
         a = L.GlgAttnArgs()
         B, Lq, _ = q.shape
@@ -145,6 +145,7 @@ class CudaOps:
         a.q_batch, a.k_batch, a.v_batch, a.o_batch = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
         a.B, a.heads, a.d_head, a.Lq, a.Lk = B, heads, d_head, Lq, Lk
         a.scale = float(d_head) ** -0.5
+        a.causal = 1 if causal else 0
         L.check(self._c.glg_attention(C.byref(a), self._stream()), "glg_attention")
         self._note("attention", 4.0 * B * heads * Lq * Lk * d_head, 2.0 * B * heads * d_head * (2 * Lq + 2 * Lk))
 
@@ -244,6 +245,22 @@ class CudaOps:
         yp, _, cpy, ldy = _rows_view(y)
         L.check(self._c.glg_layernorm_rows(xp, ldx, yp, ldy, gamma.data_ptr(), beta.data_ptr(), rows, C, cpy, eps, self._stream()), "glg_layernorm_rows")
         self._note("layernorm_rows", 0.0, 4.0 * rows * C)
+
+    def layernorm_rows_f32(self, x, y, gamma, beta, eps: float):
+        """LayerNorm of bf16 rows x [rows, C] -> fp32 y [rows, C]."""
+        xp, rows, Cc, ldx = _rows_view(x)
+        yp, _, _, ldy = _rows_view(y)
+        assert y.dtype == torch.float32
+        L.check(self._c.glg_layernorm_rows_f32(xp, ldx, yp, ldy, gamma.data_ptr(), beta.data_ptr(), rows, Cc, eps, self._stream()), "glg_layernorm_rows_f32")
+        self._note("layernorm_rows", 0.0, 6.0 * rows * Cc)
+
+    def embed_tokens(self, ids, table, pos, out):
+        """out[b, l] = table[ids[b, l]] + pos[l]  (ids int64 [B, L]; table fp32 [V, C]; pos fp32 [L, C]; out bf16 [B*L, C])."""
+        B, Lt = ids.shape
+        assert ids.dtype == torch.int64 and ids.is_contiguous() and table.is_contiguous() and pos.is_contiguous() and pos.shape[0] >= Lt
+        op, _, Cc, ldo = _rows_view(out)
+        L.check(self._c.glg_embed_tokens(ids.data_ptr(), table.data_ptr(), table.shape[0], pos.data_ptr(), op, ldo, B, Lt, Cc, self._stream()), "glg_embed_tokens")
+        self._note("embed_tokens")
 
     def dwconv7_ln(self, x, y, w, bias, gamma, beta, B: int, H: int, W: int, C: int, eps: float):
         """depthwise 7x7 + bias + LayerNorm over the first C channels: x, y bf16 rows [B*H*W, Cpad]; w fp32 [49, C]."""

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GLG_ABI_VERSION 3
+#define GLG_ABI_VERSION 4
 
 #define GLG_ACT_NONE 0
 #define GLG_ACT_SILU 1
@@ -117,6 +117,8 @@ typedef struct GlgAttnArgs {
   int64_t q_batch, k_batch, v_batch, o_batch;/* batch strides (elements) */
   int32_t B, heads, d_head, Lq, Lk;
   float scale;                               /* d_head^-0.5 */
+  int32_t causal;                            /* ABI v4: 1 = query row i attends to keys [0, i] only (the CLIP text encoder's causal
+                                                mask, transformers CLIPTextTransformer); needs Lk <= 128 (short-key kernel) */
 } GlgAttnArgs;
 int glg_attention(const GlgAttnArgs* args, void* stream);
 
@@ -184,6 +186,13 @@ int glg_patchify_nhwc(const void* x, int64_t ldx, void* out, int64_t ldo, int32_
  * channels-last tensor; two-pass statistics in registers); y columns [C, Cpad) are written as zeros (K padding). In place is fine. */
 int glg_layernorm_rows(const void* x, int64_t ldx, void* y, int64_t ldy, const float* gamma, const float* beta, int64_t rows,
                        int32_t C, int32_t Cpad, float eps, void* stream);
+/* same, fp32 output (no padding columns): the final LayerNorm of the CLIP text encoder -> last_hidden_state. */
+int glg_layernorm_rows_f32(const void* x, int64_t ldx, float* y, int64_t ldy, const float* gamma, const float* beta, int64_t rows,
+                           int32_t C, float eps, void* stream);
+/* Text-encoder input rows (ldm/modules/encoders/modules.py:157-160 -> transformers CLIPTextEmbeddings):
+ * out[b, l, :] = bf16(table[ids[b, l], :] + pos[l, :]);  ids int64 [B, L], table fp32 [vocab, C], pos fp32 [L, C]. */
+int glg_embed_tokens(const int64_t* ids, const float* table, int64_t vocab, const float* pos, void* out, int64_t ldo, int32_t B, int32_t L,
+                     int32_t C, void* stream);
 /* ConvNeXt block front (convnext.py:40-43): depthwise 7x7 pad 3 + bias, then LayerNorm over channels, one pass.
  * x / y NHWC bf16; w fp32 packed [49][C] (tap-major); y columns [C, Cpad) are zeros. */
 int glg_dwconv7_ln(const void* x, int64_t ldx, void* y, int64_t ldy, const float* w, const float* bias, const float* gamma,

@@ -49,6 +49,21 @@ for mode in modes:
                     chk = f"  rel-L2 vs first {((out.float() - ref).norm() / ref.norm()).item():.2e}"
             print(f"mode {mode} poly {poly}/8 stagger {stag:4d} {name:5s}: {us:7.1f} us  {fl / us / 1e6:6.1f} TFLOP/s{chk}", flush=True)
 ops.lib.glg_debug_attn_mode(0); ops.lib.glg_debug_attn_poly_share(0)
+if os.environ.get("VARS"):
+    ops.lib.glg_debug_attn_mode(5); ops.lib.glg_debug_attn_poly_share(2)
+    ref2 = None
+    for var in (0, 1, 2, 3, 5, 7, 0):
+        ops.lib.glg_debug_attn_tc3_variant(var)
+        for name, Lk in (("self", T), ("fuser", T + G)):
+            us = timeit(lambda: ops.attention(qkv[:, :T, :C], qkv[:, :Lk, C:2 * C], qkv[:, :Lk, 2 * C:], out, heads, d))
+            chk = ""
+            if name == "self":
+                ops.attention(qkv[:, :T, :C], qkv[:, :T, C:2 * C], qkv[:, :T, 2 * C:], out, heads, d); torch.cuda.synchronize()
+                if ref2 is None:
+                    ref2 = out.float().clone()
+                chk = f"  rel-L2 vs variant 0 {((out.float() - ref2).norm() / ref2.norm()).item():.2e}"
+            print(f"tc3 poly 2/8 variant {var} {name:5s}: {us:7.1f} us  {4.0 * Bt * heads * T * Lk * d / us / 1e6:6.1f} TFLOP/s{chk}", flush=True)
+    ops.lib.glg_debug_attn_tc3_variant(0); ops.lib.glg_debug_attn_mode(0); ops.lib.glg_debug_attn_poly_share(0)
 if os.environ.get("KO"):
     ops.lib.glg_debug_attn_mode(5)
     for ko in (0, 1, 2, 4, 8, 12, 14, 16, 17, 49):

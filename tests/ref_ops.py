@@ -79,7 +79,7 @@ class RefOps:
             stats_out[:, :, 0] = sv.sum(2).t()                       # slot-major [S, M, 2]
             stats_out[:, :, 1] = (sv * sv).sum(2).t()
 
-    def attention(self, q, k, v, out, heads, d_head):
+    def attention(self, q, k, v, out, heads, d_head, causal=False):
         self.launches += 1
         B, Lq, _ = q.shape
         Lk = k.shape[1]
@@ -87,6 +87,8 @@ class RefOps:
         kf = k.float().reshape(B, Lk, heads, d_head).permute(0, 2, 1, 3)
         vf = v.float().reshape(B, Lk, heads, d_head).permute(0, 2, 1, 3)
         sim = torch.einsum("bhic,bhjc->bhij", qf, kf) * (d_head ** -0.5)
+        if causal:
+            sim = sim.masked_fill(torch.ones(Lq, Lk, dtype=torch.bool, device=sim.device).triu(1), float("-inf"))
         o = torch.einsum("bhij,bhjc->bhic", sim.softmax(dim=-1), vf)
         out.copy_(o.permute(0, 2, 1, 3).reshape(B, Lq, heads * d_head).to(out.dtype))
 
@@ -110,6 +112,16 @@ class RefOps:
         v = F.layer_norm(x[..., :C].float(), (C,), gamma.float(), beta.float(), eps)
         y.zero_()
         y[..., :C] = v.to(y.dtype)
+
+    def layernorm_rows_f32(self, x, y, gamma, beta, eps):
+        self.launches += 1
+        C = x.shape[-1]
+        y.copy_(F.layer_norm(x.float(), (C,), gamma.float(), beta.float(), eps).reshape(y.shape))
+
+    def embed_tokens(self, ids, table, pos, out):
+        self.launches += 1
+        Lt = ids.shape[1]
+        out.copy_((table.float()[ids] + pos.float()[:Lt][None]).reshape(out.shape).to(out.dtype))
 
     def dwconv7_ln(self, x, y, w, bias, gamma, beta, B, H, W, C, eps):
         self.launches += 1

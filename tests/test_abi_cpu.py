@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert getattr(so, name) is not None
     L = lib.load()
-    assert L.glg_abi_version() == 3
+    assert L.glg_abi_version() == 4
     assert L.glg_launch_count() == 0
 
 

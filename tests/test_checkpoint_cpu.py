@@ -32,9 +32,17 @@ def test_checkpoint_round_trip(tmp_path):
     path = os.path.join(str(tmp_path), "gligen.pth")
     from ldm.models.diffusion.ldm import LatentDiffusion
     dsd = LatentDiffusion(linear_start=0.00085, linear_end=0.012, timesteps=1000).state_dict()      # schedule buffers, as in a real checkpoint
-    CK.save_ckpt(path, _config(), sd, autoencoder_sd=vsd, diffusion_sd=dsd)
+    from gligen_b200.clip_text import TINY_CLIP_TEXT, synthetic_clip_state_dict
+    cfg_all = _config()
+    cfg_all["text_encoder"] = {"target": "ldm.modules.encoders.modules.FrozenCLIPEmbedder", "params": {"text_config": "tiny_clip_text"}}
+    tsd = synthetic_clip_state_dict(TINY_CLIP_TEXT, 0)
+    tsd["transformer.text_model.embeddings.position_ids"] = torch.arange(77)[None]          # buffer older transformers releases save
+    CK.save_ckpt(path, cfg_all, sd, autoencoder_sd=vsd, text_encoder_sd=tsd, diffusion_sd=dsd)
     model, vae, text, diffusion, config = CK.load_ckpt(path, device="cpu", with_text_encoder=False)
     assert type(model).__module__ == "ldm.modules.diffusionmodules.openaimodel" and text is None
+    _, _, text, _, _ = CK.load_ckpt(path, device="cpu")
+    k = "transformer.text_model.encoder.layers.1.self_attn.q_proj.weight"
+    assert type(text).__module__ == "ldm.modules.encoders.modules" and torch.equal(text.state_dict()[k], tsd[k])
     got = model.state_dict()
     assert set(got) == set(sd) and all(torch.equal(got[k], sd[k]) for k in sd)
     assert model.grounding_tokenizer_input is not None and hasattr(model.grounding_tokenizer_input, "prepare")

@@ -337,6 +337,30 @@ def test_attention(ops, ref, B, heads, d, Lq, Lk, mode, path):
     assert_close(out, out_r, rel=1e-2, max_rel=5e-2, what=f"attention d={d} {Lq}x{Lk} {mode}")
 
 
+@pytest.mark.parametrize("var", [1, 2, 3, 5, 7])
+def test_attention_tc3_variants(ops, ref, var):
+    """three-tile kernel, FMA-pipe share 2/8, with the measured variants of the per-tile chain (lane-0 mbarrier waits, exponentials
+    before the wait for the previous P.V, lane-0 waits in the issuer warps): same results as the torch statement."""
+    B, heads, d, Lq, Lk = 2, 8, 40, 1024, 1054
+    C = heads * d
+    qkv = rnd(B, Lk, 3 * C) * 2.0
+    q, k, v = qkv[:, :Lq, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+    out = torch.zeros(B, Lq, C, device="cuda:0", dtype=torch.bfloat16)
+    out_r = torch.zeros_like(out)
+    ops.lib.glg_debug_attn_mode(5)
+    ops.lib.glg_debug_attn_poly_share(2)
+    ops.lib.glg_debug_attn_tc3_variant(var)
+    try:
+        ops.attention(q, k, v, out, heads, d)
+        torch.cuda.synchronize()
+    finally:
+        ops.lib.glg_debug_attn_mode(0)
+        ops.lib.glg_debug_attn_poly_share(0)
+        ops.lib.glg_debug_attn_tc3_variant(0)
+    ref.attention(q, k, v, out_r, heads, d)
+    assert_close(out, out_r, rel=1e-2, max_rel=5e-2, what=f"attention tc3 variant {var}")
+
+
 @pytest.mark.parametrize("mode", [4, 5])
 @pytest.mark.parametrize("poly", [1, 2, 3])
 def test_attention_fma_pipe_exp2(ops, ref, poly, mode):
