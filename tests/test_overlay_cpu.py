@@ -41,6 +41,8 @@ SCRIPT = textwrap.dedent('''
     assert H.__file__.startswith(%(repo)r)
     import ldm.modules.diffusionmodules.hed_grounding_net as HN, ldm.modules.diffusionmodules.sem_grounding_downsampler as SD
     assert HN.__file__.startswith(%(repo)r) and SD.__file__.startswith(%(repo)r)
+    E = instantiate_from_config.__globals__["get_obj_from_str"]("ldm.modules.encoders.modules.FrozenCLIPEmbedder")     # config['text_encoder']
+    assert sys.modules[E.__module__].__file__.startswith(%(repo)r)
     import ldm.modules.diffusionmodules.grounding_net_example as EX       # a reference-only module next to them still resolves
     assert EX.__file__.startswith(%(ref)r)
     # the reference VAE decoder actually runs in this overlay (tiny config)
