@@ -27,7 +27,15 @@ def _case(name, B, max_objs, tmp_path, scales=(1.0, 0.0)):
         mask = draw_masks_from_boxes(batch["boxes"], cfg.image_size).to(DEV)
         extra = torch.cat([inp["z0"].to(DEV) * mask, mask], dim=1)
     eng = model.engine()
-    N = (batch["points"] if cfg.tokenizer == "keypoint" else batch["boxes"]).shape[1]
+    gextra = None
+    if cfg.spatial:
+        from gligen_b200.spec import SPATIAL_MAP_KEY
+        gmap = batch[SPATIAL_MAP_KEY[cfg.tokenizer]]
+        gextra = gmap
+        eng._n_objs(grounding)                 # tells the engine the map size the static buffers are planned for
+        N = cfg.spatial_tokens
+    else:
+        N = (batch["points"] if cfg.tokenizer == "keypoint" else batch["boxes"]).shape[1]
     path = os.path.join(str(tmp_path), f"{name}.glgplan")
     info = export_plan(eng, 2 * B, N, ctx.shape[1], path)
     plan = NativePlan(path)
@@ -38,7 +46,10 @@ def _case(name, B, max_objs, tmp_path, scales=(1.0, 0.0)):
     if cfg.inpaint_mode:
         plan.write("in:extra", torch.cat([extra, extra]))
     z = lambda t: torch.cat([t, torch.zeros_like(t)])
-    if cfg.tokenizer == "keypoint":
+    if cfg.spatial:
+        plan.write("in:map", z(gmap)); plan.write("in:gmask", z(batch["mask"]))
+        plan.write("in:extra_map", torch.cat([gmap, gmap]))              # the uncond rows keep grounding_extra_input (plms.py:118)
+    elif cfg.tokenizer == "keypoint":
         plan.write("in:coords", z(batch["points"])); plan.write("in:masks", z(batch["masks"]))
     else:
         plan.write("in:coords", z(batch["boxes"])); plan.write("in:masks", z(batch["masks"]))
@@ -49,7 +60,8 @@ def _case(name, B, max_objs, tmp_path, scales=(1.0, 0.0)):
             plan.write("in:feat1", z(batch["image_embeddings"])); plan.write("in:fmask1", z(batch["image_masks"]))
     for scale in scales:
         set_alpha_scale(model, scale)
-        e_c, e_u = model.forward_cfg(dict(x=x, timesteps=ts, context=ctx, grounding_input=grounding, inpainting_extra_input=extra), uc)
+        e_c, e_u = model.forward_cfg(dict(x=x, timesteps=ts, context=ctx, grounding_input=grounding, inpainting_extra_input=extra,
+                                          grounding_extra_input=gextra), uc)
         want = torch.cat([e_c, e_u]).clone()
         plan.write("W:gates", eng.W["gates"])                  # scale * tanh(alpha): the host owns the scheduled-sampling scale
         plan.run(static_part=True, fuser_on=scale != 0.0)
@@ -61,7 +73,7 @@ def _case(name, B, max_objs, tmp_path, scales=(1.0, 0.0)):
     return info
 
 
-@pytest.mark.parametrize("name,max_objs", [("tiny", 6), ("tiny_text_image", 5), ("tiny_keypoint", 34), ("tiny_inpaint", 6)])
+@pytest.mark.parametrize("name,max_objs", [("tiny", 6), ("tiny_text_image", 5), ("tiny_keypoint", 34), ("tiny_inpaint", 6), ("tiny_sem", 0), ("tiny_hed", 0)])
 def test_exported_plan_matches_python_engine_tiny(name, max_objs, tmp_path):
     info = _case(name, 2, max_objs, tmp_path)
     assert info["ops"] > 300
