@@ -469,7 +469,9 @@ int attention_tc3(const GlgAttnArgs* a, cudaStream_t st) {
   // setter override it; the two-warpgroup kernel keeps its own default (0).
   int poly = g_attn_tc2_poly;
   if (poly < 0) { const char* e = getenv("GLG_ATTN_POLY"); poly = e ? atoi(e) : 2; }
-  if (g_attn_tc3_var < 0) { const char* e = getenv("GLG_ATTN_TC3_VAR"); g_attn_tc3_var = e ? atoi(e) : 0; }
+  // measured (profiles/r2_attention_l0.md, level 0, 2B = 8): variant 0 389.2 us, 1 (lane-0 waits) 434.0, 2 (exponentials before the
+  // P.V wait) 385.9, 3 413.9, 5 / 7 (lane-0 waits in the issuer warps) 653 / 647 -> default 2
+  if (g_attn_tc3_var < 0) { const char* e = getenv("GLG_ATTN_TC3_VAR"); g_attn_tc3_var = e ? atoi(e) : 2; }
   const int var = g_attn_tc3_var;
   switch (dpad) {
     case 16: return launch_attn_tc3<16, 0>(tq, tk, tv, p, a->B, st);

@@ -63,7 +63,7 @@ if os.environ.get("VARS"):
                     ref2 = out.float().clone()
                 chk = f"  rel-L2 vs variant 0 {((out.float() - ref2).norm() / ref2.norm()).item():.2e}"
             print(f"tc3 poly 2/8 variant {var} {name:5s}: {us:7.1f} us  {4.0 * Bt * heads * T * Lk * d / us / 1e6:6.1f} TFLOP/s{chk}", flush=True)
-    ops.lib.glg_debug_attn_tc3_variant(0); ops.lib.glg_debug_attn_mode(0); ops.lib.glg_debug_attn_poly_share(0)
+    ops.lib.glg_debug_attn_tc3_variant(2); ops.lib.glg_debug_attn_mode(0); ops.lib.glg_debug_attn_poly_share(0)
 if os.environ.get("KO"):
     ops.lib.glg_debug_attn_mode(5)
     for ko in (0, 1, 2, 4, 8, 12, 14, 16, 17, 49):

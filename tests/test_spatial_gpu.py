@@ -116,7 +116,12 @@ def test_conv2d_small(ops, ref, B, Cin, Cout, Hs, virtual, k, stride, pad, silu)
     Ho = (Hv + 2 * pad - k) // stride + 1
     y, y_r = torch.zeros(B, Cout, Ho, Ho, device=DEV), torch.zeros(B, Cout, Ho, Ho, device=DEV)
     ops.conv2d_small(x, w, bias, y, k, stride, pad, silu, virtual=virtual)
-    ref.conv2d_small(x, w, bias, y_r, k, stride, pad, silu, virtual=virtual)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False          # the checker must be fp32 (cuDNN convolutions default to TF32: 3e-4 off)
+    try:
+        ref.conv2d_small(x, w, bias, y_r, k, stride, pad, silu, virtual=virtual)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
     assert_close(y, y_r, rel=1e-5, max_rel=1e-4, what="conv2d_small")
 
 
