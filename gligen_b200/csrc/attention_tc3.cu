@@ -75,7 +75,8 @@ __device__ __forceinline__ float ex2_poly3(float x) {
 // POLY: of every 8 score pairs, the last POLY pairs take their exp2 from ex2_poly3 instead of the MUFU
 // KO (timing experiments only, results are wrong): 1 no exp2 (plain FMA instead), 2 K / V tiles loaded only for the first ring
 // pass, 4 no P.V MMAs, 8 no QK^T MMAs, 16 no TMEM score loads, 32 no P store, 64 clock probes of CTA (0,0,0)
-// VAR (measured variants of the per-tile chains, profiles/r2_attention_l0.md; 4 = the issuer warps' waits by lane 0 only):
+// VAR (measured variants of the per-tile chains, profiles/r2_attention_l0.md; 4 = the issuer warps' waits by lane 0 only;
+// 8 / 16 = busy-polling (mbarrier.test_wait) waits in the softmax / issuer warps):
 //   1  mbarrier waits by lane 0 only + __syncwarp (32 lanes polling the same mbarrier serialise in the shared-memory pipe)
 //   2  the exponentials of the whole tile are computed BEFORE the wait for P.V of the previous tile (only the P stores and the rare
 //      O rescale need it), taking that wait off the per-tile critical path
@@ -188,8 +189,10 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, DPAD, true);    // B (V) is MN-major
       const bool leader = elect_one();
       const uint32_t sQg = sQ + g * Q_BYTES;
-      auto mbar_wait_i = [&](uint32_t bar, uint32_t parity) {      // VAR & 4: the issuer warps' waits by lane 0 only
-        if (VAR & 4) {
+      auto mbar_wait_i = [&](uint32_t bar, uint32_t parity) {      // VAR & 4: the issuer warps' waits by lane 0 only; & 16: busy polls
+        if (VAR & 16) {
+          mbar_wait_spin(bar, parity);
+        } else if (VAR & 4) {
           if (lane == 0) mbar_wait(bar, parity);
           __syncwarp();
         } else {
@@ -254,7 +257,9 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       while (clock64() < t_end) {}
     }
     auto wait_bar = [&](uint32_t bar, uint32_t parity) {
-      if (VAR & 1) {
+      if (VAR & 8) {
+        mbar_wait_spin(bar, parity);
+      } else if (VAR & 1) {
         if (lane == 0) mbar_wait(bar, parity);
         __syncwarp();
       } else {
@@ -486,6 +491,9 @@ int attention_tc3(const GlgAttnArgs* a, cudaStream_t st) {
             case 3: return launch_attn_tc3<48, 2, 0, 3>(tq, tk, tv, p, a->B, st);
             case 5: return launch_attn_tc3<48, 2, 0, 5>(tq, tk, tv, p, a->B, st);
             case 7: return launch_attn_tc3<48, 2, 0, 7>(tq, tk, tv, p, a->B, st);
+            case 10: return launch_attn_tc3<48, 2, 0, 10>(tq, tk, tv, p, a->B, st);
+            case 18: return launch_attn_tc3<48, 2, 0, 18>(tq, tk, tv, p, a->B, st);
+            case 26: return launch_attn_tc3<48, 2, 0, 26>(tq, tk, tv, p, a->B, st);
             default: return launch_attn_tc3<48, 2>(tq, tk, tv, p, a->B, st);
           }
         case 3: return launch_attn_tc3<48, 3>(tq, tk, tv, p, a->B, st);

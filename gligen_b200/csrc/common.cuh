@@ -49,6 +49,18 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return done;
 }
+// non-suspending poll (mbarrier.test_wait): the thread keeps its issue slot instead of being parked by the hardware
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -70,6 +82,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
   }
+}
+
+// Busy-polling wait (no hardware suspend between polls): lowest wake-up latency, at the price of issue slots.  Falls back to the
+// suspending wait (with its watchdog) after 4096 polls.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
+  for (int i = 0; i < 4096; ++i)
+    if (mbar_test_wait(bar, parity)) return;
+  mbar_wait(bar, parity);
 }
 
 // One leader lane of a fully converged warp.  The single-thread roles (TMA producer, MMA issuer) run the whole warp

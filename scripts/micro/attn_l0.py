@@ -52,7 +52,7 @@ ops.lib.glg_debug_attn_mode(0); ops.lib.glg_debug_attn_poly_share(0)
 if os.environ.get("VARS"):
     ops.lib.glg_debug_attn_mode(5); ops.lib.glg_debug_attn_poly_share(2)
     ref2 = None
-    for var in (0, 1, 2, 3, 5, 7, 0):
+    for var in [int(v) for v in os.environ.get("VARLIST", "0,1,2,3,5,7,0").split(",")]:
         ops.lib.glg_debug_attn_tc3_variant(var)
         for name, Lk in (("self", T), ("fuser", T + G)):
             us = timeit(lambda: ops.attention(qkv[:, :T, :C], qkv[:, :Lk, C:2 * C], qkv[:, :Lk, 2 * C:], out, heads, d))

@@ -337,7 +337,7 @@ def test_attention(ops, ref, B, heads, d, Lq, Lk, mode, path):
     assert_close(out, out_r, rel=1e-2, max_rel=5e-2, what=f"attention d={d} {Lq}x{Lk} {mode}")
 
 
-@pytest.mark.parametrize("var", [0, 1, 3, 5, 7])
+@pytest.mark.parametrize("var", [0, 1, 3, 5, 7, 10, 18, 26])
 def test_attention_tc3_variants(ops, ref, var):
     """three-tile kernel, FMA-pipe share 2/8, with the measured variants of the per-tile chain (lane-0 mbarrier waits, exponentials
     before the wait for the previous P.V, lane-0 waits in the issuer warps): same results as the torch statement."""
