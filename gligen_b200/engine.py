@@ -354,7 +354,7 @@ class Engine:
         ds_planes = None
         if cfg.spatial:
             from . import spatial
-            spatial.emit_tokenizer(self, P, Bt, self._map_shape, objs[0])
+            spatial.emit_tokenizer(self, P, Bt, objs[0])
             if cfg.ds_out_dim:
                 ds_planes = spatial.emit_downsampler(self, P, Bt)
         else:

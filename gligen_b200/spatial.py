@@ -19,7 +19,7 @@ from typing import Dict
 
 import torch
 
-from .spec import CONVNEXT_TINY_DEPTHS as DEPTHS, CONVNEXT_TINY_DIMS as DIMS, UNetConfig
+from .spec import CONVNEXT_TINY_DEPTHS as DEPTHS, CONVNEXT_TINY_DIMS as DIMS
 
 ACT_NONE, ACT_SILU, ACT_GELU = 0, 1, 2
 _PN, _CX = "position_net", "position_net.convnext_tiny_backbone"
@@ -82,7 +82,7 @@ def pack(engine, sd: Dict[str, torch.Tensor]) -> None:
             W[f"ds.l{li}.b"] = f(sd[f"downsample_net.layers.{li}.bias"])
 
 
-def emit_tokenizer(engine, P, Bt: int, map_shape, objs: torch.Tensor) -> None:
+def emit_tokenizer(engine, P, Bt: int, objs: torch.Tensor) -> None:
     """Static plan steps: P.inp["map"] fp32 [Bt, Cm, Hm, Wm], P.inp["gmask"] fp32 [Bt]  ->  objs bf16 [Bt * n, out_dim]."""
     cfg, ops, W = engine.cfg, engine.ops, engine.W
     R, n = cfg.tok_resize, cfg.spatial_tokens
