@@ -21,14 +21,15 @@ int check_launch(const char* what) {
   if (e != cudaSuccess) return set_error(std::string(what) + ": " + cudaGetErrorString(e));
   return 0;
 }
-bool pdl_enabled() {
+int pdl_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("GLG_PDL");
-    v = e ? (atoi(e) != 0) : 0;     // measured on B200: no gain for this launch mix (profiles/), so opt-in
+    v = e ? atoi(e) : 0;            // measured on B200: no gain for this launch mix (profiles/), so opt-in
   }
-  return v != 0;
+  return v;
 }
+bool pdl_enabled() { return pdl_mode() != 0; }
 }  // namespace glg
 
 extern "C" int glg_abi_version(void) { return GLG_ABI_VERSION; }

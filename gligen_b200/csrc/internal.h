@@ -18,6 +18,8 @@ int get_tmap_bf16(CUtensorMap* out, const void* ptr, int rank, const uint64_t* d
 int get_tmap_bf16_sw(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box, int swizzle_bytes);
 int num_sms();
 bool pdl_enabled();     // GLG_PDL env (default off: measured neutral-to-negative for this launch mix)
+int pdl_mode();         // 0 off, 1 every launch, 2 only launches whose grid leaves SMs idle (fewer CTAs than SMs): their prologue
+                        // (launch latency, barrier init, TMEM allocation) overlaps the tail of the kernel before them
 
 // Launch with programmatic dependent launch (and optionally a thread-block cluster along x).
 template <typename... KArgs, typename... Args>
@@ -27,7 +29,8 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[2];
   int n = 0;
-  if (pdl_enabled()) {
+  const int pm = pdl_mode();
+  if (pm == 1 || (pm == 2 && (long long)grid.x * grid.y * grid.z < (long long)num_sms())) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;
