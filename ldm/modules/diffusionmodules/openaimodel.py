@@ -128,10 +128,18 @@ class UNetModel(ParamNode):
 
     # ---- weights ---------------------------------------------------------------------------------
     def load_state_dict(self, state_dict, strict=True, **kw):
+        conv, key = self.input_blocks[0][0], "input_blocks.0.0.weight"
+        if key in state_dict and self.downsample_net is not None and conv.weight.shape[1] != state_dict[key].shape[1] \
+                and state_dict[key].shape[1] == self.cfg.first_conv_in:
+            # a spatial-map model whose first conv was swapped for SD's 4-channel one (restore_first_conv_from_SD) gets its
+            # (4 + d)-channel GLIGEN conv back with the new weights
+            conv.weight = nn.Parameter(torch.zeros_like(state_dict[key], device=conv.weight.device), requires_grad=False)
         out = super().load_state_dict(state_dict, strict=strict, **kw)
         self._engine_stale = True
         self._masters_valid = True
         self._forget_first_conv_swap()
+        if self.downsample_net is not None:
+            self.first_conv_type = "GLIGEN"
         return out
 
     def _forget_first_conv_swap(self):

@@ -99,3 +99,21 @@ def test_drop_in_surface():
         assert null[key].shape == inp["batch"][key].shape and float(null[key].abs().sum()) == 0 and null["mask"].shape == (2,)
         with pytest.raises(RuntimeError):
             model(input)                 # CUDA only: no CPU fallback
+        # the SD first-conv swap narrows the module's conv to 4 channels (like the reference); loading a checkpoint afterwards restores it
+        import os
+        from conftest import GOLD
+        if cfg.model_channels == 320:
+            continue                     # the bundled SD conv has 320 output channels: only full-size models can take it
+        sdw = {"weight": torch.randn(cfg.model_channels, 4, 3, 3), "bias": torch.randn(cfg.model_channels)}
+        cwd = os.getcwd()
+        import tempfile
+        with tempfile.TemporaryDirectory() as d:
+            torch.save(sdw, os.path.join(d, "SD_input_conv_weight_bias.pth"))
+            os.chdir(d)
+            try:
+                model.restore_first_conv_from_SD()
+            finally:
+                os.chdir(cwd)
+        assert model.first_conv_type == "SD" and model.input_blocks[0][0].weight.shape[1] == 4
+        model.load_state_dict(synthetic_state_dict(cfg, 0))
+        assert model.first_conv_type == "GLIGEN" and model.input_blocks[0][0].weight.shape[1] == cfg.first_conv_in
