@@ -162,3 +162,22 @@ def test_read_official_ckpt_splits_by_prefix(tmp_path):
     assert list(out["autoencoder"]) == ["decoder.conv_in.bias"]
     assert sorted(out["unexpected"]) == ["model_ema.decay", "model_ema.num_updates"]
     assert sorted(out["diffusion"]) == ["alphas_cumprod", "betas"]
+
+
+def test_c_host_example_builds(tmp_path):
+    """examples/host_c/unet_host.c (a host without Python over the engine-level C ABI) compiles against include/gligen_b200.h and
+    links against the library with plain gcc - no CUDA headers, no torch."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    from gligen_b200 import lib as L
+    L.load()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(str(tmp_path), "unet_host")
+    r = subprocess.run(["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "host_c", "unet_host.c"),
+                        "-L", os.path.join(root, "gligen_b200"), "-lgligen_b200", f"-Wl,-rpath,{os.path.join(root, 'gligen_b200')}", "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr

@@ -82,3 +82,45 @@ def test_exported_plan_matches_python_engine_tiny(name, max_objs, tmp_path):
 def test_exported_plan_matches_python_engine_sd14(tmp_path):
     info = _case("sd14_box_text", 1, 30, tmp_path, scales=(1.0,))
     print(f"\nsd14 plan: {info}")
+
+
+def test_c_host_replays_plan(tmp_path):
+    """The plan of the tiny model replayed by examples/host_c/unet_host.c (plain C, no Python, no CUDA headers) gives the Python-driven
+    engine's eps bit for bit."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(str(tmp_path), "unet_host")
+    r = subprocess.run(["gcc", "-O2", "-I", os.path.join(root, "include"), os.path.join(root, "examples", "host_c", "unet_host.c"),
+                        "-L", os.path.join(root, "gligen_b200"), "-lgligen_b200", f"-Wl,-rpath,{os.path.join(root, 'gligen_b200')}", "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    B, G = 2, 6
+    cfg, model = build_model("tiny", DEV)
+    inp = synth.make_inputs(cfg, B, G, seed=4)
+    ts = torch.tensor([981, 401], dtype=torch.long, device=DEV)
+    x, ctx, uc = inp["x"].to(DEV), inp["context"].to(DEV), inp["uc"].to(DEV)
+    batch = to_device(inp["batch"], DEV)
+    grounding = model.grounding_tokenizer_input.prepare(batch)
+    e_c, e_u = model.forward_cfg(dict(x=x, timesteps=ts, context=ctx, grounding_input=grounding, inpainting_extra_input=None), uc)
+    want = torch.cat([e_c, e_u]).clone().cpu()
+    eng = model.engine()
+    path = os.path.join(str(tmp_path), "tiny.glgplan")
+    export_plan(eng, 2 * B, G, ctx.shape[1], path)
+    z = lambda t: torch.cat([t, torch.zeros_like(t)])
+    files = {"in:x": torch.cat([x, x]), "in:t": torch.cat([ts, ts]), "in:context": torch.cat([ctx, uc]), "in:coords": z(batch["boxes"]),
+             "in:masks": z(batch["masks"]), "in:feat0": z(batch["text_embeddings"]), "in:fmask0": z(batch["masks"]), "W:gates": eng.W["gates"]}
+    args = []
+    for name, t in files.items():
+        fn = os.path.join(str(tmp_path), name.replace(":", "_") + ".bin")
+        t.contiguous().cpu().numpy().tofile(fn)
+        args.append(f"{name}={fn}")
+    outp = os.path.join(str(tmp_path), "out.bin")
+    r = subprocess.run([exe, path, outp] + args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    import numpy as np
+    got = torch.from_numpy(np.fromfile(outp, dtype=np.float32)).view(want.shape)
+    assert torch.equal(got, want), f"C host: max diff {(got - want).abs().max().item():.3e}"
+    print("\n" + r.stdout.strip())
