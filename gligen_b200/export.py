@@ -52,7 +52,10 @@ def _registry(eng, P) -> List[Tuple[str, torch.Tensor, bool]]:
 
 
 def export_plan(eng, rows: int, n_objs: int, n_ctx: int, path: str) -> Dict[str, int]:
-    """Write the plan for (rows, n_objs, n_ctx) - rows = 2B when cond + uncond run as one batch.  Returns counts."""
+    """Write the plan for (rows, n_objs, n_ctx) - rows = 2B when cond + uncond run as one batch.  Returns counts.
+    Spatial-map models: n_objs = cfg.spatial_tokens, and the engine must have seen one grounded call (or `eng._n_objs(grounding)`)
+    so that it knows the (C, H, W) of the conditioning map its static buffers are sized for; the named inputs are then
+    "in:map", "in:gmask" and "in:extra_map"."""
     P = eng._plan(rows, n_objs, n_ctx)
     reg = _registry(eng, P)
     spans = []
