@@ -108,6 +108,7 @@ SD14_NORMAL = replace(SD14_BOX_TEXT, tokenizer="normal", ds_out_dim=8)
 SD14_SEM = replace(SD14_BOX_TEXT, tokenizer="sem", ds_out_dim=8)
 # tiny UNets behind the real ConvNeXt-tiny (the backbone has one size); 128-pixel tokenizer input -> 16 tokens
 TINY_HED = replace(TINY, tokenizer="hed", ds_out_dim=1, tok_resize=128, image_size=64)     # hed: bicubic straight to 64 x 64 (hard-coded in the reference)
+TINY_CANNY = replace(TINY, tokenizer="canny", ds_out_dim=8, tok_resize=128, ds_resize=64)
 TINY_DEPTH = replace(TINY, tokenizer="depth", ds_out_dim=8, tok_resize=128, ds_resize=64)
 TINY_NORMAL = replace(TINY, tokenizer="normal", ds_out_dim=8, tok_resize=128, ds_resize=64)
 TINY_SEM = replace(TINY, tokenizer="sem", ds_out_dim=8, tok_resize=128, ds_resize=64, sem_in_dim=24)
@@ -122,7 +123,7 @@ NAMED_CONFIGS = {
     "tiny_keypoint": TINY_KEYPOINT,
     "tiny_inpaint": TINY_INPAINT,
     "sd14_hed": SD14_HED, "sd14_canny": SD14_CANNY, "sd14_depth": SD14_DEPTH, "sd14_normal": SD14_NORMAL, "sd14_sem": SD14_SEM,
-    "tiny_hed": TINY_HED, "tiny_depth": TINY_DEPTH, "tiny_normal": TINY_NORMAL, "tiny_sem": TINY_SEM,
+    "tiny_hed": TINY_HED, "tiny_canny": TINY_CANNY, "tiny_depth": TINY_DEPTH, "tiny_normal": TINY_NORMAL, "tiny_sem": TINY_SEM,
 }
 
 

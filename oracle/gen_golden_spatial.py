@@ -82,8 +82,10 @@ if __name__ == "__main__":
     ap.add_argument("--full", action="store_true", help="also the full-size SD-1.4 hed / sem models (1.07 B parameters each)")
     a = ap.parse_args()
     os.chdir(ROOT)
-    for name in ("tiny_hed", "tiny_depth", "tiny_normal", "tiny_sem"):
-        run(name, 2, 11)
+    only = os.environ.get("ONLY")
+    for name in ("tiny_hed", "tiny_canny", "tiny_depth", "tiny_normal", "tiny_sem"):
+        if only is None or name in only.split(","):
+            run(name, 2, 11)
     if a.full:
         for name in ("sd14_hed", "sd14_sem"):
             run(name, 1, 12, plms=(name == "sd14_hed"))

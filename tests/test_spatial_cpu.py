@@ -17,7 +17,7 @@ from gligen_b200.spec import NAMED_CONFIGS, SPATIAL_MAP_KEY, synthetic_state_dic
 from oracle import unet_oracle as UO
 from ref_ops import RefOps
 
-TINY = ["tiny_hed", "tiny_depth", "tiny_normal", "tiny_sem"]
+TINY = ["tiny_hed", "tiny_canny", "tiny_depth", "tiny_normal", "tiny_sem"]
 
 
 def _load(name):
