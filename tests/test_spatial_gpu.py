@@ -161,7 +161,7 @@ def _run(name):
     return cfg, model, g, inp
 
 
-@pytest.mark.parametrize("name", ["tiny_hed", "tiny_depth", "tiny_normal", "tiny_sem"])
+@pytest.mark.parametrize("name", ["tiny_hed", "tiny_canny", "tiny_depth", "tiny_normal", "tiny_sem"])
 def test_forward_tiny_spatial(name):
     _run(name)
 
