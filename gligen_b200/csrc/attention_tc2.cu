@@ -51,7 +51,7 @@ __device__ __forceinline__ float ex2_approx2(float x) {
   return y;
 }
 
-// exp2 on the FMA / ALU pipes (Cody-Waite split + degree-3 polynomial on [-0.5, 0.5]; relative error 1e-4, far below the
+// exp2 on the FMA / ALU pipes (Cody-Waite split + degree-3 polynomial on [-0.5, 0.5]; relative error 1.2e-4 mean / 7.9e-4 max, below the
 // bf16 rounding of P): a share of the exponentials is taken off the MUFU pipe, which bounds this kernel (16 exp2 / clk / SM).
 __device__ __forceinline__ float ex2_poly(float x) {
   x = fmaxf(x, -125.0f);
